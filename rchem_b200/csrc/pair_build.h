@@ -1,0 +1,61 @@
+// pair_build.h -- primitive-pair quantities of one shell pair (host, setup only).
+//
+// Every expression that feeds the REFERENCE Boys argument is formed exactly as
+// coulomb_repulsion does (cints.c:85-96): product centres by product_center_1D
+// (cints.c:391-394), 1./gamma by an IEEE division.  This file must be compiled without
+// FMA contraction (-ffp-contract=off), like the reference's x86-64 build.
+#pragma once
+#include <cmath>
+#include <vector>
+
+#include "basis_model.h"
+#include "eri_core.h"
+
+namespace rchem {
+
+// Primitive pairs of (A,B), A-primitive major: k = i*nprim(B) + j.
+inline void build_prim_pairs(const Shell& A, const Shell& B, std::vector<PrimPair>* out) {
+  out->clear();
+  const double dx = A.ctr[0] - B.ctr[0], dy = A.ctr[1] - B.ctr[1], dz = A.ctr[2] - B.ctr[2];
+  const double rab2 = dx * dx + dy * dy + dz * dz;  // dist2, cints.c:282-285
+  for (size_t i = 0; i < A.exps.size(); ++i)
+    for (size_t j = 0; j < B.exps.size(); ++j) {
+      const double aa = A.exps[i], ab = B.exps[j];
+      PrimPair pp;
+      pp.zeta = aa + ab;
+      pp.rzeta = 1. / pp.zeta;
+      pp.Px = (aa * A.ctr[0] + ab * B.ctr[0]) / (aa + ab);
+      pp.Py = (aa * A.ctr[1] + ab * B.ctr[1]) / (aa + ab);
+      pp.Pz = (aa * A.ctr[2] + ab * B.ctr[2]) / (aa + ab);
+      // exp(-aa*ab*rab2/gamma) as in cints.c:113, the 1/gamma of cints.c:112, and the
+      // contraction coefficient x norm of both primitives
+      pp.pref = A.cn[i] * B.cn[j] * std::exp(-aa * ab * rab2 / pp.zeta) / pp.zeta;
+      out->push_back(pp);
+    }
+}
+
+// exact Boys table for boys_exact (eri_core.h): rows x = i/kBoysPerUnit, columns m
+inline void build_boys_table(std::vector<double>* table) {
+  table->assign((size_t)kBoysRows * kBoysCols, 0.0);
+  for (int i = 0; i < kBoysRows; ++i) {
+    const long double x = (long double)i / kBoysPerUnit;
+    // top order by the all-positive series e^-x sum_k (2x)^k / ((2m+1)(2m+3)..(2m+2k+1)),
+    // lower orders by the stable downward recursion
+    const int mtop = kBoysCols - 1;
+    long double term = 1.0L / (2 * mtop + 1), sum = term;
+    for (int k = 1; k < 2000; ++k) {
+      term *= 2.0L * x / (2 * mtop + 2 * k + 1);
+      sum += term;
+      if (term < 1e-24L * sum) break;
+    }
+    const long double ex = expl(-x);
+    long double f = ex * sum;
+    (*table)[(size_t)i * kBoysCols + mtop] = (double)f;
+    for (int m = mtop; m > 0; --m) {
+      f = (2.0L * x * f + ex) / (2 * m - 1);
+      (*table)[(size_t)i * kBoysCols + m - 1] = (double)f;
+    }
+  }
+}
+
+}  // namespace rchem

@@ -1,0 +1,268 @@
+#!/usr/bin/env python3
+"""Code generator for the per-class ERI recurrences (Head-Gordon--Pople scheme).
+
+For every angular-momentum class (la lb|lc ld) with la>=lb, lc>=ld, (la,lb)>=(lc,ld),
+la<=LMAX this script emits straight-line C++ (usable from CUDA device code and from a
+plain host compiler) for
+
+  * the Obara--Saika vertical recurrence (VRR) that turns the scaled Boys values
+    F_0..F_L of ONE primitive quartet into the [e0|f0] targets, la<=|e|<=la+lb,
+    lc<=|f|<=lc+ld, and adds them into the contraction accumulators, and
+  * the horizontal recurrence (HRR) that turns the contracted [e0|f0] block into the
+    Cartesian (ab|cd) block of the shell quartet.
+
+The reference evaluates the same recurrences recursively (chgp.c:44-135 contr_hrr /
+contr_vrr, chgp.c:412-586 vrr_recursive); here every intermediate is computed once.
+The VRR picks, per target, the Cartesian direction with the fewest terms (2, 3 or 4),
+which is the "minimal HGP" operation-count model of SURVEY.md section 8(d).
+
+Component order inside a shell follows shell::get_ijk_list (shell.rs:1-12).
+
+Outputs (into --outdir):
+  eri_class_<abcd>.inc   one per class: struct EriClass<la,lb,lc,ld> specialisation
+  eri_classes.h          includes + class table
+  flops.json             op counts of the emitted code (mul/add = 1, fma = 2)
+"""
+import argparse
+import json
+import os
+import sys
+
+LMAX = 2
+AX = "xyz"
+
+
+def cart(l):
+    """shell::get_ijk_list (shell.rs:1-12)"""
+    return [(l + 1 - a, a - b, b - 1) for a in range(1, l + 2) for b in range(1, a + 1)]
+
+
+def dec(t, i):
+    return tuple(v - (1 if k == i else 0) for k, v in enumerate(t))
+
+
+def inc(t, i):
+    return tuple(v + (1 if k == i else 0) for k, v in enumerate(t))
+
+
+class Emitter:
+    def __init__(self):
+        self.lines = []
+        self.n = 0
+        self.flops = 0
+
+    def tmp(self, expr, flops):
+        name = f"t{self.n}"
+        self.n += 1
+        self.lines.append(f"const double {name} = {expr};")
+        self.flops += flops
+        return name
+
+
+class VRR:
+    """Memoised OS vertical recurrence for [e0|f0]^(m)."""
+
+    def __init__(self, em):
+        self.em = em
+        self.memo = {}
+        self.gmemo = {}
+
+    def val(self, e, f, m):
+        key = (e, f, m)
+        if key in self.memo:
+            return self.memo[key]
+        if sum(e) == 0 and sum(f) == 0:
+            r = f"F[{m}]"
+        elif sum(f) > 0:
+            r = self._reduce(e, f, m, ket=True)
+        else:
+            r = self._reduce(e, f, m, ket=False)
+        self.memo[key] = r
+        return r
+
+    def gdiff(self, e, f, m, ket):
+        """[e|f]^(m) - (rho/eta or rho/zeta) [e|f]^(m+1), shared between targets"""
+        key = (e, f, m, ket)
+        if key in self.gmemo:
+            return self.gmemo[key]
+        a = self.val(e, f, m)
+        b = self.val(e, f, m + 1)
+        fac = "roe" if ket else "roz"
+        r = self.em.tmp(f"fma(-{fac}, {b}, {a})", 2)
+        self.gmemo[key] = r
+        return r
+
+    def _reduce(self, e, f, m, ket):
+        tgt = f if ket else e
+        # choose the direction with the fewest terms
+        best = None
+        for i in range(3):
+            if tgt[i] == 0:
+                continue
+            low = dec(tgt, i)
+            cost = 2 + (1 if low[i] > 0 else 0)
+            if ket and e[i] > 0:
+                cost += 1
+            # tie-break: prefer directions whose lower terms are likely shared (larger i last)
+            if best is None or cost < best[0]:
+                best = (cost, i)
+        i = best[1]
+        low = dec(tgt, i)
+        if ket:
+            e0, f0 = e, low
+            c1, c2 = f"QC{AX[i]}", f"WQ{AX[i]}"
+        else:
+            e0, f0 = low, f
+            c1, c2 = f"PA{AX[i]}", f"WP{AX[i]}"
+        v0 = self.val(e0, f0, m)
+        v1 = self.val(e0, f0, m + 1)
+        expr = f"fma({c1}, {v0}, {c2} * {v1})"
+        flops = 3
+        if low[i] > 0:
+            if ket:
+                g = self.gdiff(e0, dec(f0, i), m, True)
+                coef = f"oo2e" if low[i] == 1 else f"({low[i]}.0 * oo2e)"
+            else:
+                g = self.gdiff(dec(e0, i), f0, m, False)
+                coef = f"oo2z" if low[i] == 1 else f"({low[i]}.0 * oo2z)"
+            expr = f"fma({coef}, {g}, {expr})"
+            flops += 2
+        if ket and e[i] > 0:
+            v = self.val(dec(e, i), f0, m + 1)
+            coef = f"oo2ze" if e[i] == 1 else f"({e[i]}.0 * oo2ze)"
+            expr = f"fma({coef}, {v}, {expr})"
+            flops += 2
+        return self.em.tmp(expr, flops)
+
+
+def gen_class(la, lb, lc, ld):
+    L = la + lb + lc + ld
+    es = [e for l in range(la, la + lb + 1) for e in cart(l)]
+    fs = [f for l in range(lc, lc + ld + 1) for f in cart(l)]
+    tindex = {}
+    for e in es:
+        for f in fs:
+            tindex[(e, f)] = len(tindex)
+    nt = len(tindex)
+
+    # ---- VRR ---------------------------------------------------------------
+    em = Emitter()
+    v = VRR(em)
+    acc_lines = []
+    for (e, f), idx in tindex.items():
+        name = v.val(e, f, 0)
+        acc_lines.append(f"acc[{idx}] += {name};")
+    vrr_flops = em.flops + nt  # one add per target for the contraction
+    vrr_body = em.lines + acc_lines
+
+    # ---- HRR ---------------------------------------------------------------
+    hm = Emitter()
+    bmemo = {}
+
+    def hb(a, b, f):
+        key = (a, b, f)
+        if key in bmemo:
+            return bmemo[key]
+        if sum(b) == 0:
+            r = f"acc[{tindex[(a, f)]}]"
+        else:
+            i = next(k for k in range(3) if b[k] > 0)
+            hi = hb(inc(a, i), dec(b, i), f)
+            lo = hb(a, dec(b, i), f)
+            r = hm.tmp(f"fma(AB{AX[i]}, {lo}, {hi})", 2)
+        bmemo[key] = r
+        return r
+
+    kmemo = {}
+
+    def hk(a, b, c, d):
+        key = (a, b, c, d)
+        if key in kmemo:
+            return kmemo[key]
+        if sum(d) == 0:
+            r = hb(a, b, c)
+        else:
+            i = next(k for k in range(3) if d[k] > 0)
+            hi = hk(a, b, inc(c, i), dec(d, i))
+            lo = hk(a, b, c, dec(d, i))
+            r = hm.tmp(f"fma(CD{AX[i]}, {lo}, {hi})", 2)
+        kmemo[key] = r
+        return r
+
+    out_lines = []
+    ca, cb, cc, cd = cart(la), cart(lb), cart(lc), cart(ld)
+    nout = len(ca) * len(cb) * len(cc) * len(cd)
+    o = 0
+    for a in ca:
+        for b in cb:
+            for c in cc:
+                for d in cd:
+                    out_lines.append(f"out[{o}] = {hk(a, b, c, d)};")
+                    o += 1
+    hrr_flops = hm.flops
+    hrr_body = hm.lines + out_lines
+
+    tag = f"{la}{lb}{lc}{ld}"
+    src = []
+    src.append(f"// generated by rchem_b200/gen/gen_eri.py -- do not edit")
+    src.append(f"// class ({'spdfg'[la]}{'spdfg'[lb]}|{'spdfg'[lc]}{'spdfg'[ld]}): {nt} VRR targets, "
+               f"{nout} integrals, emitted flops/primitive {vrr_flops}, HRR flops {hrr_flops}")
+    src.append(f"template <> struct EriClass<{la}, {lb}, {lc}, {ld}> {{")
+    src.append(f"  static constexpr int kL = {L};")
+    src.append(f"  static constexpr int kTargets = {nt};")
+    src.append(f"  static constexpr int kOut = {nout};")
+    src.append(f"  static constexpr int kVrrFlops = {vrr_flops};")
+    src.append(f"  static constexpr int kHrrFlops = {hrr_flops};")
+    src.append("  RCHEM_HD static void vrr(const double* __restrict__ F, const VrrGeom& g, "
+               "double* __restrict__ acc) {")
+    used = "\n".join(vrr_body)
+    for nm in ["PAx", "PAy", "PAz", "WPx", "WPy", "WPz", "QCx", "QCy", "QCz", "WQx", "WQy", "WQz",
+               "oo2z", "oo2e", "oo2ze", "roz", "roe"]:
+        if nm in used:
+            src.append(f"    const double {nm} = g.{nm};")
+    src += ["    " + l for l in vrr_body]
+    src.append("  }")
+    src.append("  RCHEM_HD static void hrr(const double* __restrict__ acc, double ABx, double ABy, "
+               "double ABz, double CDx, double CDy, double CDz, double* __restrict__ out) {")
+    src.append("    (void)ABx; (void)ABy; (void)ABz; (void)CDx; (void)CDy; (void)CDz;")
+    src += ["    " + l for l in hrr_body]
+    src.append("  }")
+    src.append("};")
+    return tag, "\n".join(src) + "\n", dict(targets=nt, out=nout, vrr_flops=vrr_flops,
+                                             hrr_flops=hrr_flops)
+
+
+def classes(lmax=LMAX):
+    pairs = [(a, b) for a in range(lmax + 1) for b in range(a + 1)]
+    out = []
+    for i, (la, lb) in enumerate(pairs):
+        for (lc, ld) in pairs[: i + 1]:
+            out.append((la, lb, lc, ld))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--outdir", default=os.path.join(os.path.dirname(__file__), "..", "csrc", "gen"))
+    args = ap.parse_args()
+    os.makedirs(args.outdir, exist_ok=True)
+    table = {}
+    tags = []
+    for (la, lb, lc, ld) in classes():
+        tag, src, info = gen_class(la, lb, lc, ld)
+        with open(os.path.join(args.outdir, f"eri_class_{tag}.inc"), "w") as fh:
+            fh.write(src)
+        table[tag] = info
+        tags.append((la, lb, lc, ld, tag))
+    with open(os.path.join(args.outdir, "flops.json"), "w") as fh:
+        json.dump(table, fh, indent=1, sort_keys=True)
+    with open(os.path.join(args.outdir, "eri_class_list.h"), "w") as fh:
+        fh.write("// generated by rchem_b200/gen/gen_eri.py -- do not edit\n")
+        fh.write("// X(la, lb, lc, ld, tag)\n#define RCHEM_ERI_CLASSES(X) \\\n")
+        fh.write(" \\\n".join(f"  X({la}, {lb}, {lc}, {ld}, {tag})" for la, lb, lc, ld, tag in tags))
+        fh.write("\n")
+    print(f"generated {len(tags)} classes into {os.path.abspath(args.outdir)}", file=sys.stderr)
+
+
+if __name__ == "__main__":
+    main()

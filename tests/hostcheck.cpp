@@ -1,0 +1,144 @@
+// hostcheck.cpp -- TEST-ONLY host build of the per-quartet arithmetic (eri_core.h + the
+// generated recurrences), so the recurrences, the Boys restatement, the prefactors and the
+// component ordering can be checked against the oracle in the CPU-only container.
+// It is compiled into tests/_build/libhostcheck.so by tests/conftest.py and is never part of,
+// nor loaded by, the product library (which has no CPU path).
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../rchem_b200/csrc/basis_model.h"
+#include "../rchem_b200/csrc/eri_core.h"
+#include "../rchem_b200/csrc/pair_build.h"
+#include "../rchem_b200/csrc/gen/eri_class_list.h"
+
+namespace rchem {
+#include "../rchem_b200/csrc/gen/eri_class_0000.inc"
+#include "../rchem_b200/csrc/gen/eri_class_1000.inc"
+#include "../rchem_b200/csrc/gen/eri_class_1010.inc"
+#include "../rchem_b200/csrc/gen/eri_class_1100.inc"
+#include "../rchem_b200/csrc/gen/eri_class_1110.inc"
+#include "../rchem_b200/csrc/gen/eri_class_1111.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2000.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2010.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2011.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2020.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2100.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2110.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2111.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2120.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2121.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2200.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2210.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2211.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2220.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2221.inc"
+#include "../rchem_b200/csrc/gen/eri_class_2222.inc"
+
+template <class C, int BOYS>
+void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const Shell& Cc,
+                   const Shell& D, const double* table, double* out) {
+  std::vector<PrimPair> bra, ket;
+  build_prim_pairs(A, B, &bra);
+  build_prim_pairs(Cc, D, &ket);
+  std::vector<double> acc(C::kTargets, 0.0);
+  for (const PrimPair& k : ket)
+    for (const PrimPair& b : bra)
+      primitive_quartet<C, BOYS>(b, k, A.ctr[0], A.ctr[1], A.ctr[2], Cc.ctr[0], Cc.ctr[1],
+                                 Cc.ctr[2], table, acc.data());
+  C::hrr(acc.data(), A.ctr[0] - B.ctr[0], A.ctr[1] - B.ctr[1], A.ctr[2] - B.ctr[2],
+         Cc.ctr[0] - D.ctr[0], Cc.ctr[1] - D.ctr[1], Cc.ctr[2] - D.ctr[2], out);
+  const int na = ncart(A.l), nb = ncart(B.l), nc = ncart(Cc.l), nd = ncart(D.l);
+  for (int a = 0; a < na; ++a)
+    for (int b = 0; b < nb; ++b)
+      for (int c = 0; c < nc; ++c)
+        for (int d = 0; d < nd; ++d)
+          out[((a * nb + b) * nc + c) * nd + d] *= ss.compscale[A.l][a] * ss.compscale[B.l][b] *
+                                                   ss.compscale[Cc.l][c] * ss.compscale[D.l][d];
+}
+}  // namespace rchem
+
+using namespace rchem;
+
+static Basis from_flat(int n, const double* origins, const int32_t* powers,
+                       const int32_t* prim_offset, const double* exps, const double* coefs,
+                       const double* norms) {
+  Basis b;
+  for (int i = 0; i < n; ++i) {
+    CGTO g;
+    for (int d = 0; d < 3; ++d) { g.origin[d] = origins[3 * i + d]; g.powers[d] = powers[3 * i + d]; }
+    for (int p = prim_offset[i]; p < prim_offset[i + 1]; ++p) {
+      PGTO pg;
+      for (int d = 0; d < 3; ++d) { pg.origin[d] = g.origin[d]; pg.powers[d] = g.powers[d]; }
+      pg.exponent = exps[p];
+      pg.norm = norms[p];
+      g.primitives.push_back(pg);
+      g.coefs.push_back(coefs[p]);
+    }
+    b.cgtos.push_back(g);
+  }
+  return b;
+}
+
+extern "C" int hostcheck_nshells(int n, const double* origins, const int32_t* powers,
+                                 const int32_t* prim_offset, const double* exps,
+                                 const double* coefs, const double* norms, int32_t* l_out,
+                                 int32_t* bf0_out) {
+  Basis b = from_flat(n, origins, powers, prim_offset, exps, coefs, norms);
+  ShellSet ss;
+  std::string err;
+  if (!group_shells(b, &ss, &err)) return -1;
+  for (size_t i = 0; i < ss.shells.size(); ++i) {
+    if (l_out) l_out[i] = ss.shells[i].l;
+    if (bf0_out) bf0_out[i] = ss.shells[i].bf0;
+  }
+  return (int)ss.shells.size();
+}
+
+// Evaluates the Cartesian block of shell quartet (sa sb|sc sd); the shells must already be in
+// class order (la>=lb, lc>=ld, (la,lb)>=(lc,ld)).  Returns the number of integrals or <0.
+extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32_t* powers,
+                                       const int32_t* prim_offset, const double* exps,
+                                       const double* coefs, const double* norms, int sa, int sb,
+                                       int sc, int sd, int boys, double* out) {
+  Basis b = from_flat(n, origins, powers, prim_offset, exps, coefs, norms);
+  ShellSet ss;
+  std::string err;
+  if (!group_shells(b, &ss, &err)) return -1;
+  static std::vector<double> table;
+  if (table.empty()) build_boys_table(&table);
+  const Shell &A = ss.shells[sa], &B = ss.shells[sb], &C = ss.shells[sc], &D = ss.shells[sd];
+#define X(la, lb, lc, ld, tag)                                                              \
+  if (A.l == la && B.l == lb && C.l == lc && D.l == ld) {                                   \
+    if (boys == kBoysReference)                                                             \
+      shell_quartet<EriClass<la, lb, lc, ld>, kBoysReference>(ss, A, B, C, D, table.data(), out); \
+    else                                                                                    \
+      shell_quartet<EriClass<la, lb, lc, ld>, kBoysExact>(ss, A, B, C, D, table.data(), out);     \
+    return EriClass<la, lb, lc, ld>::kOut;                                                  \
+  }
+  RCHEM_ERI_CLASSES(X)
+#undef X
+  return -2;
+}
+
+extern "C" void hostcheck_boys(int boys, int L, double x, double* F) {
+  static std::vector<double> table;
+  if (table.empty()) build_boys_table(&table);
+  // L <= 8
+  if (boys == kBoysReference) {
+    switch (L) {
+      case 0: boys_reference<0>(x, F); break;
+      case 2: boys_reference<2>(x, F); break;
+      case 4: boys_reference<4>(x, F); break;
+      default: boys_reference<8>(x, F); break;
+    }
+  } else {
+    switch (L) {
+      case 0: boys_exact<0>(x, table.data(), F); break;
+      case 2: boys_exact<2>(x, table.data(), F); break;
+      case 4: boys_exact<4>(x, table.data(), F); break;
+      default: boys_exact<8>(x, table.data(), F); break;
+    }
+  }
+}
