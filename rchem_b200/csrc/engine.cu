@@ -1,0 +1,773 @@
+// engine.cu -- host runtime behind the C ABI (include/rchem_eri.h): shell-pair batches in HBM,
+// Schwarz bounds, the implicit screened quartet list, kernel launches, J/K finalisation.
+//
+// Reference correspondence: this file plays the role of the loop nests in src/basis.rs
+// (JK_direct 383-428, build_I 430-460, JK_inmem 462-484) -- re-designed as batched GPU work.
+// There is no CPU compute path: without a CUDA device every compute call fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/rchem_eri.h"
+#include "basis_model.h"
+#include "eri_kernel.cuh"
+#include "gen/eri_class_list.h"
+#include "pair_build.h"
+
+namespace rchem {
+
+// launchers, one per class translation unit
+#define X(la, lb, lc, ld, tag) \
+  cudaError_t launch_eri_##tag(int, int, const EriTask&, unsigned, cudaStream_t);
+RCHEM_ERI_CLASSES(X)
+#undef X
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int fail_public(int code, const std::string& msg) { return fail(code, msg); }
+#define CUDA_OK(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(RCHEM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));     \
+  } while (0)
+
+// SURVEY section 8(d) flop model: per primitive quartet P, per contracted quartet H.
+struct FlopModel { int la, lb, lc, ld, P, H; };
+static const FlopModel kFlopModel[] = {
+    {0, 0, 0, 0, 51, 0},       {1, 0, 0, 0, 66, 0},        {1, 0, 1, 0, 118, 0},
+    {1, 1, 0, 0, 115, 18},     {1, 1, 1, 0, 281, 54},      {1, 1, 1, 1, 792, 324},
+    {2, 0, 0, 0, 112, 0},      {2, 0, 1, 0, 239, 0},       {2, 0, 1, 1, 627, 108},
+    {2, 0, 2, 0, 609, 0},      {2, 1, 0, 0, 201, 36},      {2, 1, 1, 0, 516, 108},
+    {2, 1, 1, 1, 1486, 648},   {2, 1, 2, 0, 1438, 216},    {2, 1, 2, 1, 3286, 1224},
+    {2, 2, 0, 0, 355, 158},    {2, 2, 1, 0, 964, 474},     {2, 2, 1, 1, 2834, 2070},
+    {2, 2, 2, 0, 2741, 948},   {2, 2, 2, 1, 6263, 3824},   {2, 2, 2, 2, 12280, 10586},
+};
+static const FlopModel* flop_model(int la, int lb, int lc, int ld) {
+  for (const FlopModel& f : kFlopModel)
+    if (f.la == la && f.lb == lb && f.lc == lc && f.ld == ld) return &f;
+  return nullptr;
+}
+
+static EriLaunchFn find_launcher(int la, int lb, int lc, int ld) {
+#define X(a, b, c, d, tag) \
+  if (la == a && lb == b && lc == c && ld == d) return launch_eri_##tag;
+  RCHEM_ERI_CLASSES(X)
+#undef X
+  return nullptr;
+}
+
+struct Batch {
+  int la = 0, lb = 0, K2 = 0, npairs = 0, stride = 0;
+  std::vector<int> shA, shB;
+  std::vector<double> Q;
+  double* d_prim = nullptr;
+  double* d_geom = nullptr;
+  int* d_idx = nullptr;
+  BatchView view() const { return BatchView{d_prim, d_geom, d_idx, npairs, stride, K2}; }
+};
+
+struct TaskTable {
+  int bra = 0, ket = 0;
+  long long nwarps = 0, nquartets = 0, nquartets_all = 0;
+  long long* d_prefix = nullptr;
+  int* d_nq = nullptr;
+  std::vector<long long> h_prefix;  // kept for rchem_quartet_list
+  std::vector<int> h_nq;
+};
+
+__global__ void finalize_jk_kernel(const double* __restrict__ Jh, const double* __restrict__ Kh,
+                                   double* __restrict__ JK, int N) {
+  // J = Jh + Jh^T, K = Kh + Kh^T  (the two transposed halves of the 8-fold digestion)
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nn = (size_t)N * N;
+  if (idx >= nn) return;
+  const size_t i = idx / N, j = idx % N;
+  JK[idx] = Jh[idx] + Jh[j * N + i];
+  JK[nn + idx] = Kh[idx] + Kh[j * N + i];
+}
+
+// JK_inmem (basis.rs:462-484) in ONE pass over the tensor: element I[i][j][k][l] feeds
+// J[i][j] (with D[k][l]) and K[i][k] (with D[j][l]).  One block per (i,j) row of N^2 values;
+// one warp per k sums over l.  HBM-bound: 8 N^4 bytes read once.
+__global__ void jk_inmem_kernel(const double* __restrict__ I, const double* __restrict__ D,
+                                double* __restrict__ JK, int N) {
+  const size_t nn = (size_t)N * N;
+  const int i = blockIdx.x / N, j = blockIdx.x % N;
+  const double* row = I + (size_t)blockIdx.x * nn;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  double jsum = 0.0;
+  for (int k = warp; k < N; k += nwarps) {
+    double ks = 0.0;
+    for (int l = lane; l < N; l += 32) {
+      const double v = row[(size_t)k * N + l];
+      jsum = fma(v, D[(size_t)k * N + l], jsum);
+      ks = fma(v, D[(size_t)j * N + l], ks);
+    }
+    ks = warp_sum(ks);
+    if (lane == 0) atomicAdd(JK + nn + (size_t)i * N + k, ks);
+  }
+  jsum = warp_sum(jsum);
+  if (lane == 0) atomicAdd(JK + (size_t)i * N + j, jsum);
+}
+
+// materialises the implicit quartet list of one task: (p, q) for q < nq[p]
+__global__ void quartet_list_kernel(const long long* __restrict__ qprefix,
+                                    const int* __restrict__ nq, int npairs, long long pair_off_b,
+                                    long long pair_off_k, long long* __restrict__ out) {
+  const int p = blockIdx.x;
+  if (p >= npairs) return;
+  const long long base = qprefix[p];
+  for (int q = threadIdx.x; q < nq[p]; q += blockDim.x) {
+    out[2 * (base + q)] = pair_off_b + p;
+    out[2 * (base + q) + 1] = pair_off_k + q;
+  }
+}
+
+}  // namespace rchem
+
+using namespace rchem;
+
+struct rchem_basis {
+  Basis basis;
+  ShellSet shells;
+  int N = 0;
+  int nprim = 0;
+  // options
+  int boys = kBoysReference;
+  double tau = 0.0;
+  int device = 0;
+  // device state
+  bool ready = false;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::vector<Batch> batches;
+  std::vector<TaskTable> tasks;
+  double tasks_tau = -1.0;
+  double* d_boys = nullptr;
+  double *d_D = nullptr, *d_Jh = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  rchem_stats stats{};
+};
+
+namespace {
+
+int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
+  // order: permutation of pair slots (Schwarz-descending once Q is known)
+  const int np = bt.npairs;
+  bt.stride = (np + 31) / 32 * 32;
+  const size_t st = bt.stride;
+  std::vector<double> prim(6 * (size_t)bt.K2 * st, 0.0), geom(6 * st, 0.0);
+  std::vector<int> idx(3 * st, 0);
+  std::vector<PrimPair> pps;
+  std::vector<int> shA(np), shB(np);
+  std::vector<double> Q(bt.Q.empty() ? 0 : np);
+  for (int s = 0; s < np; ++s) {
+    const int src = order[s];
+    const Shell& A = h->shells.shells[bt.shA[src]];
+    const Shell& B = h->shells.shells[bt.shB[src]];
+    shA[s] = bt.shA[src];
+    shB[s] = bt.shB[src];
+    if (!bt.Q.empty()) Q[s] = bt.Q[src];
+    build_prim_pairs(A, B, &pps);
+    for (int k = 0; k < bt.K2; ++k) {
+      const PrimPair& pp = pps[k];
+      const double f[6] = {pp.zeta, pp.rzeta, pp.Px, pp.Py, pp.Pz, pp.pref};
+      for (int c = 0; c < 6; ++c) prim[((size_t)c * bt.K2 + k) * st + s] = f[c];
+    }
+    for (int d = 0; d < 3; ++d) {
+      geom[d * st + s] = A.ctr[d];
+      geom[(3 + d) * st + s] = A.ctr[d] - B.ctr[d];
+    }
+    idx[s] = A.bf0;
+    idx[st + s] = B.bf0;
+    idx[2 * st + s] = (bt.shA[src] == bt.shB[src]) ? 1 : 0;
+  }
+  // padding slots replicate pair 0 so stray reads stay finite
+  for (int s = np; s < (int)st; ++s) {
+    for (size_t c = 0; c < 6 * (size_t)bt.K2; ++c) prim[c * st + s] = prim[c * st];
+    for (int c = 0; c < 6; ++c) geom[c * st + s] = geom[c * st];
+    for (int c = 0; c < 3; ++c) idx[c * st + s] = idx[c * st];
+  }
+  bt.shA.swap(shA);
+  bt.shB.swap(shB);
+  if (!bt.Q.empty()) bt.Q.swap(Q);
+  if (!bt.d_prim) {
+    CUDA_OK(cudaMalloc(&bt.d_prim, prim.size() * sizeof(double)));
+    CUDA_OK(cudaMalloc(&bt.d_geom, geom.size() * sizeof(double)));
+    CUDA_OK(cudaMalloc(&bt.d_idx, idx.size() * sizeof(int)));
+  }
+  CUDA_OK(cudaMemcpyAsync(bt.d_prim, prim.data(), prim.size() * sizeof(double),
+                          cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(bt.d_geom, geom.data(), geom.size() * sizeof(double),
+                          cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(bt.d_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice,
+                          h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));  // host vectors die at scope exit
+  return RCHEM_OK;
+}
+
+void fill_common(const rchem_basis* h, EriTask* t) {
+  std::memset(t, 0, sizeof(*t));
+  t->N = h->N;
+  t->boys_table = h->d_boys;
+  t->nranks = 1;
+  for (int l = 0; l < 3; ++l)
+    for (int k = 0; k < 6; ++k) t->compscale[l][k] = (l <= h->shells.lmax) ? h->shells.compscale[l][k] : 1.0;
+}
+
+int ensure_ready(rchem_basis* h) {
+  if (h->ready) return RCHEM_OK;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(RCHEM_ERR_NO_DEVICE,
+                std::string("no CUDA device: librchem_b200 has no CPU path (") +
+                    cudaGetErrorString(e) + ")");
+  if (h->device < 0 || h->device >= ndev) return fail(RCHEM_ERR_INVALID_ARG, "bad device ordinal");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (h->shells.lmax > 2)
+    return fail(RCHEM_ERR_UNSUPPORTED_AM, "class kernels cover s, p and d shells only");
+  if (!h->own_stream) CUDA_OK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  if (!h->stream) h->stream = h->own_stream;
+  CUDA_OK(cudaEventCreate(&h->ev0));
+  CUDA_OK(cudaEventCreate(&h->ev1));
+
+  // exact-Boys grid
+  std::vector<double> table;
+  build_boys_table(&table);
+  CUDA_OK(cudaMalloc(&h->d_boys, table.size() * sizeof(double)));
+  CUDA_OK(cudaMemcpy(h->d_boys, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
+
+  // shell pairs -> batches keyed by (la, lb, K2); batch order = pair class, then K2 descending
+  const auto& sh = h->shells.shells;
+  std::map<std::tuple<int, int, int>, Batch> by_key;
+  for (int i = 0; i < (int)sh.size(); ++i)
+    for (int j = 0; j <= i; ++j) {
+      int a = i, b = j;
+      if (sh[a].l < sh[b].l) std::swap(a, b);
+      const int K2 = (int)(sh[a].exps.size() * sh[b].exps.size());
+      const int cls = sh[a].l * (sh[a].l + 1) / 2 + sh[b].l;
+      Batch& bt = by_key[std::make_tuple(cls, -K2, 0)];
+      bt.la = sh[a].l; bt.lb = sh[b].l; bt.K2 = K2;
+      bt.shA.push_back(a); bt.shB.push_back(b);
+    }
+  h->batches.clear();
+  for (auto& kv : by_key) {
+    kv.second.npairs = (int)kv.second.shA.size();
+    h->batches.push_back(std::move(kv.second));
+  }
+
+  // Schwarz bounds Q_ab = sqrt(max |(ab|ab)|) with the exact Boys function (so the quartet
+  // list does not depend on the Boys option), then sort every batch by Q descending.
+  for (Batch& bt : h->batches) {
+    std::vector<int> ident(bt.npairs);
+    std::iota(ident.begin(), ident.end(), 0);
+    int rc = upload_batch(h, bt, ident);
+    if (rc) return rc;
+    double* dQ = nullptr;
+    CUDA_OK(cudaMalloc(&dQ, (size_t)bt.npairs * sizeof(double)));
+    EriTask t;
+    fill_common(h, &t);
+    t.bra = t.ket = bt.view();
+    t.nwarps = (bt.npairs + 31) / 32;
+    t.same = 1;
+    t.Qout = dQ;
+    EriLaunchFn fn = find_launcher(bt.la, bt.lb, bt.la, bt.lb);
+    const unsigned grid = (unsigned)((t.nwarps + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    CUDA_OK(fn(kBoysExact, kModeSchwarz, t, grid, h->stream));
+    bt.Q.resize(bt.npairs);
+    CUDA_OK(cudaMemcpyAsync(bt.Q.data(), dQ, (size_t)bt.npairs * sizeof(double),
+                            cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaFree(dQ));
+    std::vector<int> order(bt.npairs);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bt.Q[x] > bt.Q[y]; });
+    rc = upload_batch(h, bt, order);
+    if (rc) return rc;
+  }
+
+  const size_t nn = (size_t)h->N * h->N;
+  CUDA_OK(cudaMalloc(&h->d_D, nn * sizeof(double)));
+  CUDA_OK(cudaMalloc(&h->d_Jh, 2 * nn * sizeof(double)));
+  h->d_Kh = h->d_Jh + nn;
+  CUDA_OK(cudaMalloc(&h->d_JK, 2 * nn * sizeof(double)));
+  h->ready = true;
+  return RCHEM_OK;
+}
+
+void free_tasks(rchem_basis* h) {
+  for (TaskTable& t : h->tasks) {
+    if (t.d_prefix) cudaFree(t.d_prefix);
+    if (t.d_nq) cudaFree(t.d_nq);
+  }
+  h->tasks.clear();
+  h->tasks_tau = -1.0;
+}
+
+// The implicit screened quartet list (DESIGN.md "quartet list"): for task (bra batch, ket
+// batch <= bra batch) and bra pair p the surviving kets are the prefix
+//   q < nq[p] = #{q : Q_bra[p]*Q_ket[q] >= tau}   (Q_ket descending), and q <= p when the
+// batches coincide.  Pure integer/compare work on the shared Q arrays.
+int ensure_tasks(rchem_basis* h) {
+  if (h->tasks_tau == h->tau && !h->tasks.empty()) return RCHEM_OK;
+  free_tasks(h);
+  const double tau = h->tau;
+  for (int bi = 0; bi < (int)h->batches.size(); ++bi)
+    for (int ki = 0; ki <= bi; ++ki) {
+      const Batch &B = h->batches[bi], &K = h->batches[ki];
+      TaskTable tt;
+      tt.bra = bi; tt.ket = ki;
+      tt.h_nq.resize(B.npairs);
+      tt.h_prefix.resize(B.npairs + 1);
+      tt.h_prefix[0] = 0;
+      for (int p = 0; p < B.npairs; ++p) {
+        const double qb = B.Q[p];
+        int lo = 0, hi = K.npairs;  // first q with qb*Q[q] < tau
+        while (lo < hi) {
+          const int mid = (lo + hi) / 2;
+          if (qb * K.Q[mid] >= tau) lo = mid + 1; else hi = mid;
+        }
+        int cut = lo;
+        const int full = (bi == ki) ? p + 1 : K.npairs;
+        if (bi == ki) cut = std::min(cut, p + 1);
+        tt.h_nq[p] = cut;
+        tt.h_prefix[p + 1] = tt.h_prefix[p] + (cut + 31) / 32;
+        tt.nquartets += cut;
+        tt.nquartets_all += full;
+      }
+      tt.nwarps = tt.h_prefix[B.npairs];
+      CUDA_OK(cudaMalloc(&tt.d_prefix, tt.h_prefix.size() * sizeof(long long)));
+      CUDA_OK(cudaMalloc(&tt.d_nq, std::max<size_t>(1, tt.h_nq.size()) * sizeof(int)));
+      CUDA_OK(cudaMemcpy(tt.d_prefix, tt.h_prefix.data(), tt.h_prefix.size() * sizeof(long long),
+                         cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(tt.d_nq, tt.h_nq.data(), tt.h_nq.size() * sizeof(int),
+                         cudaMemcpyHostToDevice));
+      h->tasks.push_back(std::move(tt));
+    }
+  h->tasks_tau = tau;
+  return RCHEM_OK;
+}
+
+// launches every task in `mode`; fills stats
+int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
+  rchem_stats& st = h->stats;
+  st = rchem_stats{};
+  st.n_tasks = (int)h->tasks.size();
+  CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+  for (const TaskTable& tt : h->tasks) {
+    const Batch &B = h->batches[tt.bra], &K = h->batches[tt.ket];
+    st.shell_quartets_all += tt.nquartets_all;
+    if (tt.nwarps == 0) continue;
+    EriTask t = proto;
+    t.bra = B.view();
+    t.ket = K.view();
+    t.warp_prefix = tt.d_prefix;
+    t.nq = tt.d_nq;
+    t.nwarps = tt.nwarps;
+    t.same = tt.bra == tt.ket;
+    t.rank = rank;
+    t.nranks = nranks;
+    const long long nblocks = (tt.nwarps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const long long mine = nblocks > rank ? (nblocks - rank + nranks - 1) / nranks : 0;
+    if (mine > 0x7fffffffLL) return fail(RCHEM_ERR_TOO_LARGE, "task exceeds the grid limit");
+    EriLaunchFn fn = find_launcher(B.la, B.lb, K.la, K.lb);
+    if (!fn) return fail(RCHEM_ERR_UNSUPPORTED_AM, "no kernel for this class");
+    CUDA_OK(fn(h->boys, mode, t, (unsigned)mine, h->stream));
+    if (mine > 0) st.launches += 1;
+    // statistics (the share of this rank is the block-interleaved 1/nranks slice)
+    const double share = nblocks ? (double)mine / (double)nblocks : 0.0;
+    const long long q = (long long)std::llround(tt.nquartets * share);
+    const FlopModel* fm = flop_model(B.la, B.lb, K.la, K.lb);
+    const double k4 = (double)B.K2 * K.K2;
+    st.shell_quartets += q;
+    st.prim_quartets += (long long)(q * k4);
+    st.integrals += q * (long long)(ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb));
+    if (fm) st.model_flops += q * (k4 * fm->P + fm->H);
+  }
+  CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+  return RCHEM_OK;
+}
+
+int make_basis_handle(Basis&& basis, rchem_basis** out) {
+  rchem_basis* h = new rchem_basis();
+  h->basis = std::move(basis);
+  std::string err;
+  if (!group_shells(h->basis, &h->shells, &err)) {
+    delete h;
+    return fail(RCHEM_ERR_UNSUPPORTED_LAYOUT, err);
+  }
+  h->N = (int)h->basis.cgtos.size();
+  for (const CGTO& g : h->basis.cgtos) h->nprim += (int)g.primitives.size();
+  *out = h;
+  return RCHEM_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* rchem_last_error(void) { return g_err.c_str(); }
+int rchem_version(void) { return 100; }
+
+int rchem_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(RCHEM_ERR_NO_DEVICE, cudaGetErrorString(e));
+  return n;
+}
+
+int rchem_basis_new(int natoms, const uint64_t* atomnos, const double* coords,
+                    const char* basis_set_name, rchem_basis** out) {
+  if (natoms <= 0 || !atomnos || !coords || !basis_set_name || !out)
+    return fail(RCHEM_ERR_INVALID_ARG, "rchem_basis_new: null or empty argument");
+  Basis b;
+  std::string err;
+  std::vector<uint64_t> z(atomnos, atomnos + natoms);
+  if (!basis_new(z, coords, basis_set_name, &b, &err)) return fail(RCHEM_ERR_UNKNOWN_BASIS, err);
+  return make_basis_handle(std::move(b), out);
+}
+
+int rchem_basis_create(int n, const double* origins, const int32_t* powers,
+                       const int32_t* prim_offset, const double* exps, const double* coefs,
+                       const double* norms, rchem_basis** out) {
+  if (n <= 0 || !origins || !powers || !prim_offset || !exps || !coefs || !norms || !out)
+    return fail(RCHEM_ERR_INVALID_ARG, "rchem_basis_create: null or empty argument");
+  Basis b;
+  b.name = "custom";
+  for (int i = 0; i < n; ++i) {
+    if (prim_offset[i + 1] <= prim_offset[i])
+      return fail(RCHEM_ERR_INVALID_ARG, "rchem_basis_create: CGTO without primitives");
+    CGTO g;
+    for (int d = 0; d < 3; ++d) {
+      g.origin[d] = origins[3 * i + d];
+      g.powers[d] = powers[3 * i + d];
+      if (g.powers[d] < 0) return fail(RCHEM_ERR_INVALID_ARG, "negative Cartesian power");
+    }
+    for (int p = prim_offset[i]; p < prim_offset[i + 1]; ++p) {
+      PGTO pg;
+      for (int d = 0; d < 3; ++d) { pg.origin[d] = g.origin[d]; pg.powers[d] = g.powers[d]; }
+      pg.exponent = exps[p];
+      pg.norm = norms[p];
+      if (!(pg.exponent > 0.0)) return fail(RCHEM_ERR_INVALID_ARG, "non-positive exponent");
+      g.primitives.push_back(pg);
+      g.coefs.push_back(coefs[p]);
+    }
+    b.cgtos.push_back(std::move(g));
+  }
+  return make_basis_handle(std::move(b), out);
+}
+
+void rchem_basis_destroy(rchem_basis* h) {
+  if (!h) return;
+  if (h->ready) {
+    cudaSetDevice(h->device);
+    free_tasks(h);
+    for (Batch& bt : h->batches) {
+      cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_idx);
+    }
+    cudaFree(h->d_boys); cudaFree(h->d_D); cudaFree(h->d_Jh); cudaFree(h->d_JK);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+  }
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int rchem_basis_nbf(const rchem_basis* h) { return h ? h->N : RCHEM_ERR_INVALID_ARG; }
+int rchem_basis_nprim(const rchem_basis* h) { return h ? h->nprim : RCHEM_ERR_INVALID_ARG; }
+int rchem_basis_nshells(const rchem_basis* h) {
+  return h ? (int)h->shells.shells.size() : RCHEM_ERR_INVALID_ARG;
+}
+
+int rchem_basis_export(const rchem_basis* h, double* origins, int32_t* powers,
+                       int32_t* prim_offset, double* exps, double* coefs, double* norms) {
+  if (!h) return fail(RCHEM_ERR_INVALID_ARG, "null handle");
+  int p = 0;
+  for (int i = 0; i < h->N; ++i) {
+    const CGTO& g = h->basis.cgtos[i];
+    for (int d = 0; d < 3; ++d) {
+      if (origins) origins[3 * i + d] = g.origin[d];
+      if (powers) powers[3 * i + d] = g.powers[d];
+    }
+    if (prim_offset) prim_offset[i] = p;
+    for (size_t k = 0; k < g.primitives.size(); ++k, ++p) {
+      if (exps) exps[p] = g.primitives[k].exponent;
+      if (coefs) coefs[p] = g.coefs[k];
+      if (norms) norms[p] = g.primitives[k].norm;
+    }
+  }
+  if (prim_offset) prim_offset[h->N] = p;
+  return RCHEM_OK;
+}
+
+int rchem_basis_shells(const rchem_basis* h, int32_t* l, int32_t* first_function) {
+  if (!h) return fail(RCHEM_ERR_INVALID_ARG, "null handle");
+  for (size_t i = 0; i < h->shells.shells.size(); ++i) {
+    if (l) l[i] = h->shells.shells[i].l;
+    if (first_function) first_function[i] = h->shells.shells[i].bf0;
+  }
+  return (int)h->shells.shells.size();
+}
+
+double rchem_normalization(const int32_t powers[3], double exponent) {
+  const int pw[3] = {powers[0], powers[1], powers[2]};
+  return pgto_normalization(pw, exponent);
+}
+
+int rchem_get_ijk_list(int m, int32_t* out) {
+  if (m < 0) return fail(RCHEM_ERR_INVALID_ARG, "negative angular momentum");
+  const auto v = get_ijk_list(m);
+  if (out)
+    for (size_t i = 0; i < v.size(); ++i)
+      for (int d = 0; d < 3; ++d) out[3 * i + d] = v[i][d];
+  return (int)v.size();
+}
+
+int64_t rchem_ijkl2intindex(int64_t i, int64_t j, int64_t k, int64_t l) {
+  if (i < j) std::swap(i, j);
+  if (k < l) std::swap(k, l);
+  int64_t ij = i * (i + 1) / 2 + j, kl = k * (k + 1) / 2 + l;
+  if (ij < kl) std::swap(ij, kl);
+  return ij * (ij + 1) / 2 + kl;
+}
+
+int rchem_set_option(rchem_basis* h, int key, double value) {
+  if (!h) return fail(RCHEM_ERR_INVALID_ARG, "null handle");
+  switch (key) {
+    case RCHEM_OPT_BOYS:
+      if (value != 0.0 && value != 1.0) return fail(RCHEM_ERR_INVALID_ARG, "boys must be 0 or 1");
+      h->boys = (int)value;
+      return RCHEM_OK;
+    case RCHEM_OPT_SCHWARZ_TAU:
+      if (!(value >= 0.0)) return fail(RCHEM_ERR_INVALID_ARG, "tau must be >= 0");
+      h->tau = value;
+      return RCHEM_OK;
+    case RCHEM_OPT_DEVICE:
+      if (h->ready) return fail(RCHEM_ERR_INVALID_ARG, "device is fixed after the first compute call");
+      h->device = (int)value;
+      return RCHEM_OK;
+  }
+  return fail(RCHEM_ERR_INVALID_ARG, "unknown option");
+}
+
+double rchem_get_option(const rchem_basis* h, int key) {
+  if (!h) return std::numeric_limits<double>::quiet_NaN();
+  switch (key) {
+    case RCHEM_OPT_BOYS: return h->boys;
+    case RCHEM_OPT_SCHWARZ_TAU: return h->tau;
+    case RCHEM_OPT_DEVICE: return h->device;
+  }
+  return std::numeric_limits<double>::quiet_NaN();
+}
+
+int rchem_set_stream(rchem_basis* h, void* s) {
+  if (!h) return fail(RCHEM_ERR_INVALID_ARG, "null handle");
+  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return RCHEM_OK;
+}
+
+int rchem_get_stats(const rchem_basis* h, rchem_stats* out) {
+  if (!h || !out) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
+  *out = h->stats;
+  if (h->ready && h->ev0 && h->stats.launches > 0) {
+    if (cudaEventSynchronize(h->ev1) == cudaSuccess) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) out->kernel_ms = ms;
+    }
+  }
+  return RCHEM_OK;
+}
+
+// ---------------- device-buffer entry points ---------------------------------------------
+int rchem_jk_direct_device(rchem_basis* h, const double* D_dev, double* JK_dev, int rank,
+                           int nranks) {
+  if (!h || !D_dev || !JK_dev) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(RCHEM_ERR_INVALID_ARG, "bad rank");
+  int rc = ensure_ready(h);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(h->device));
+  rc = ensure_tasks(h);
+  if (rc) return rc;
+  const size_t nn = (size_t)h->N * h->N;
+  CUDA_OK(cudaMemsetAsync(h->d_Jh, 0, 2 * nn * sizeof(double), h->stream));  // J.fill(0); K.fill(0)
+  EriTask proto;
+  fill_common(h, &proto);
+  proto.D = D_dev;
+  proto.Jh = h->d_Jh;
+  proto.Kh = h->d_Kh;
+  rc = run_tasks(h, kModeJK, proto, rank, nranks);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)((nn + 255) / 256);
+  finalize_jk_kernel<<<grid, 256, 0, h->stream>>>(h->d_Jh, h->d_Kh, JK_dev, h->N);
+  CUDA_OK(cudaGetLastError());
+  h->stats.launches += 1;
+  return RCHEM_OK;
+}
+
+int rchem_build_I_device(rchem_basis* h, double* I_dev) {
+  if (!h || !I_dev) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
+  int rc = ensure_ready(h);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(h->device));
+  rc = ensure_tasks(h);
+  if (rc) return rc;
+  const size_t n4 = (size_t)h->N * h->N * h->N * h->N;
+  CUDA_OK(cudaMemsetAsync(I_dev, 0, n4 * sizeof(double), h->stream));
+  EriTask proto;
+  fill_common(h, &proto);
+  proto.I = I_dev;
+  return run_tasks(h, kModeTensor, proto, 0, 1);
+}
+
+int rchem_jk_inmem_device(int n, const double* I_dev, const double* D_dev, double* JK_dev,
+                          void* cuda_stream) {
+  if (n <= 0 || !I_dev || !D_dev || !JK_dev) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const size_t nn = (size_t)n * n;
+  CUDA_OK(cudaMemsetAsync(JK_dev, 0, 2 * nn * sizeof(double), s));
+  jk_inmem_kernel<<<(unsigned)nn, 256, 0, s>>>(I_dev, D_dev, JK_dev, n);
+  CUDA_OK(cudaGetLastError());
+  return RCHEM_OK;
+}
+
+// ---------------- host-buffer entry points (copies inside) -------------------------------
+int rchem_jk_direct(rchem_basis* h, const double* D, double* J, double* K) {
+  if (!h || !D || !J || !K) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
+  const int N = h->N;
+  const size_t nn = (size_t)N * N;
+  double dmax = 0.0, amax = 0.0;
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < i; ++j) {
+      dmax = std::max(dmax, std::fabs(D[(size_t)i * N + j]));
+      amax = std::max(amax, std::fabs(D[(size_t)i * N + j] - D[(size_t)j * N + i]));
+    }
+  if (amax > 1e-12 * std::max(dmax, 1e-300))
+    return fail(RCHEM_ERR_ASYMMETRIC_D, "JK_direct: the density matrix must be symmetric");
+  int rc = ensure_ready(h);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemcpyAsync(h->d_D, D, nn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  rc = rchem_jk_direct_device(h, h->d_D, h->d_JK, 0, 1);
+  if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(J, h->d_JK, nn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaMemcpyAsync(K, h->d_JK + nn, nn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return RCHEM_OK;
+}
+
+int rchem_build_I(rchem_basis* h, double* I) {
+  if (!h || !I) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
+  int rc = ensure_ready(h);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(h->device));
+  const size_t n4 = (size_t)h->N * h->N * h->N * h->N;
+  size_t free_b = 0, total_b = 0;
+  CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+  if (n4 * sizeof(double) > free_b)
+    return fail(RCHEM_ERR_TOO_LARGE, "dense N^4 tensor does not fit in device memory");
+  double* dI = nullptr;
+  CUDA_OK(cudaMalloc(&dI, n4 * sizeof(double)));
+  rc = rchem_build_I_device(h, dI);
+  if (rc == RCHEM_OK) {
+    cudaError_t e = cudaMemcpyAsync(I, dI, n4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = fail(RCHEM_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(dI);
+  return rc;
+}
+
+int rchem_jk_inmem(int n, const double* I, const double* D, double* J, double* K) {
+  if (n <= 0 || !I || !D || !J || !K) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(RCHEM_ERR_NO_DEVICE, "no CUDA device: librchem_b200 has no CPU path");
+  const size_t nn = (size_t)n * n, n4 = nn * nn;
+  double *dI = nullptr, *dD = nullptr, *dJK = nullptr;
+  CUDA_OK(cudaMalloc(&dI, n4 * sizeof(double)));
+  cudaError_t e = cudaMalloc(&dD, nn * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dJK, 2 * nn * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(dI, I, n4 * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dD, D, nn * sizeof(double), cudaMemcpyHostToDevice);
+  int rc = RCHEM_OK;
+  if (e == cudaSuccess) rc = rchem_jk_inmem_device(n, dI, dD, dJK, nullptr);
+  if (e == cudaSuccess && rc == RCHEM_OK) e = cudaMemcpy(J, dJK, nn * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && rc == RCHEM_OK) e = cudaMemcpy(K, dJK + nn, nn * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dI); cudaFree(dD); cudaFree(dJK);
+  if (e != cudaSuccess) return fail(RCHEM_ERR_CUDA, cudaGetErrorString(e));
+  return rc;
+}
+
+// ---------------- screening ---------------------------------------------------------------
+int64_t rchem_schwarz(rchem_basis* h, int32_t* shell_a, int32_t* shell_b, int32_t* batch,
+                      double* Q) {
+  if (!h) return fail(RCHEM_ERR_INVALID_ARG, "null handle");
+  int rc = ensure_ready(h);
+  if (rc) return rc;
+  int64_t n = 0;
+  for (size_t bi = 0; bi < h->batches.size(); ++bi) {
+    const Batch& bt = h->batches[bi];
+    for (int p = 0; p < bt.npairs; ++p, ++n) {
+      if (shell_a) shell_a[n] = bt.shA[p];
+      if (shell_b) shell_b[n] = bt.shB[p];
+      if (batch) batch[n] = (int32_t)bi;
+      if (Q) Q[n] = bt.Q[p];
+    }
+  }
+  return n;
+}
+
+int64_t rchem_quartet_list(rchem_basis* h, int64_t* pq, int64_t capacity) {
+  if (!h) return fail(RCHEM_ERR_INVALID_ARG, "null handle");
+  int rc = ensure_ready(h);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(h->device));
+  rc = ensure_tasks(h);
+  if (rc) return rc;
+  int64_t total = 0;
+  for (const TaskTable& tt : h->tasks) total += tt.nquartets;
+  if (!pq) return total;
+  if (capacity < total) return fail(RCHEM_ERR_INVALID_ARG, "quartet list buffer too small");
+  std::vector<long long> pair_off(h->batches.size() + 1, 0);
+  for (size_t i = 0; i < h->batches.size(); ++i) pair_off[i + 1] = pair_off[i] + h->batches[i].npairs;
+  long long* d_out = nullptr;
+  CUDA_OK(cudaMalloc(&d_out, std::max<int64_t>(1, total) * 2 * sizeof(long long)));
+  int64_t off = 0;
+  for (const TaskTable& tt : h->tasks) {
+    const Batch& B = h->batches[tt.bra];
+    if (tt.nquartets == 0) continue;
+    std::vector<long long> qprefix(B.npairs + 1, 0);
+    for (int p = 0; p < B.npairs; ++p) qprefix[p + 1] = qprefix[p] + tt.h_nq[p];
+    long long* d_qp = nullptr;
+    CUDA_OK(cudaMalloc(&d_qp, qprefix.size() * sizeof(long long)));
+    CUDA_OK(cudaMemcpy(d_qp, qprefix.data(), qprefix.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    quartet_list_kernel<<<B.npairs, 128, 0, h->stream>>>(d_qp, tt.d_nq, B.npairs, pair_off[tt.bra],
+                                                          pair_off[tt.ket], d_out + 2 * off);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaFree(d_qp));
+    off += tt.nquartets;
+  }
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+  CUDA_OK(cudaMemcpy(pq, d_out, (size_t)total * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaFree(d_out));
+  return total;
+}
+
+}  // extern "C"

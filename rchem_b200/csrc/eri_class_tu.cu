@@ -1,0 +1,39 @@
+// eri_class_tu.cu -- one translation unit per angular-momentum class.
+// Compiled 21 times with -DRCHEM_LA=.. -DRCHEM_LB=.. -DRCHEM_LC=.. -DRCHEM_LD=.. and
+// -DRCHEM_TAG=<abcd> (see rchem_b200/csrc/Makefile), so the classes build in parallel.
+#include "eri_kernel.cuh"
+
+#define RCHEM_STR2(x) #x
+#define RCHEM_STR(x) RCHEM_STR2(x)
+#define RCHEM_CAT2(a, b) a##b
+#define RCHEM_CAT(a, b) RCHEM_CAT2(a, b)
+
+namespace rchem {
+
+#include RCHEM_INC
+
+template <int BOYS, int MODE>
+static cudaError_t launch_one(const EriTask& task, unsigned grid, cudaStream_t stream) {
+  eri_kernel<RCHEM_LA, RCHEM_LB, RCHEM_LC, RCHEM_LD, BOYS, MODE>
+      <<<grid, kThreads, 0, stream>>>(task);
+  return cudaGetLastError();
+}
+
+cudaError_t RCHEM_CAT(launch_eri_, RCHEM_TAG)(int boys, int mode, const EriTask& task,
+                                              unsigned grid, cudaStream_t stream) {
+  if (grid == 0) return cudaSuccess;
+  if (mode == kModeJK)
+    return boys == kBoysReference ? launch_one<kBoysReference, kModeJK>(task, grid, stream)
+                                  : launch_one<kBoysExact, kModeJK>(task, grid, stream);
+  if (mode == kModeTensor)
+    return boys == kBoysReference ? launch_one<kBoysReference, kModeTensor>(task, grid, stream)
+                                  : launch_one<kBoysExact, kModeTensor>(task, grid, stream);
+#if RCHEM_LA == RCHEM_LC && RCHEM_LB == RCHEM_LD
+  if (mode == kModeSchwarz)
+    return boys == kBoysReference ? launch_one<kBoysReference, kModeSchwarz>(task, grid, stream)
+                                  : launch_one<kBoysExact, kModeSchwarz>(task, grid, stream);
+#endif
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace rchem
