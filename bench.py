@@ -1,0 +1,428 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the ERI hot path.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A STEP is one Schwarz-screened direct J/K build (every surviving shell quartet evaluated
+once, digested into J and K, one all-reduce for N>1) of the workload below on synthetic
+input.  metric = ERI shell-quartets/s (BASELINE.json).  `value` is measured with D already
+resident in HBM; `e2e` goes through the reference-facing call with HOST buffers
+(JK_direct(J, K, basis, D): H2D of D, compute, D2H of J and K inside the timed region).
+
+The reference arm (--impl reference) times the reference's own CPU implementation of the
+path (libpyquante2's coulomb_repulsion compiled unmodified into oracle/_ref, driven by the
+restated basis.rs loop nest, OpenMP over all host cores) on a bounded seeded sample of the
+same workload's surviving shell quartets.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_waters, basis, tau, BASELINE.json config it realises)
+    "h2o96_631g": (96, "6-31G", 1e-10, "configs[4]: synthetic (H2O)_96 6-31G, N=1248, Schwarz-screened direct J/K"),
+    "h2o96_sto3g": (96, "STO-3G", 1e-10, "configs[4]: synthetic (H2O)_96 STO-3G, N=672, Schwarz-screened direct J/K"),
+    "h2o32_631g": (32, "6-31G", 1e-10, "configs[3]: synthetic (H2O)_32 6-31G, N=416, direct J/K"),
+    "h2o32_631gs": (32, "6-31G*", 1e-10, "configs[3]: synthetic (H2O)_32 6-31G*, N=608 (s/p/d), direct J/K"),
+    "h2o10_sto3g": (10, "STO-3G", 0.0, "configs[2]: synthetic (H2O)_10 STO-3G, N=70, ERI + J/K"),
+}
+DEFAULT_WORKLOAD = "h2o96_631g"
+METRIC = "ERI shell-quartets/sec (Schwarz-screened direct J/K build)"
+UNIT = "shell-quartets/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--boys", default="reference", choices=["reference", "exact"],
+                    help="reference = libpyquante2 Fgamma (1e-12 parity); exact = converged Boys")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------
+# workload + sampling of surviving shell quartets (shared by both arms)
+# ---------------------------------------------------------------------------------------
+def make_workload(name):
+    from rchem_b200 import geometry as geo
+
+    n_waters, basis, tau, desc = WORKLOADS[name]
+    z, x = geo.water_cluster(n_waters)
+    return z, x, basis, tau, desc
+
+
+def sample_shell_quartets(shell_l, shell_first, sa, sb, Q, tau, count, seed=20261017):
+    """Uniform sample of the surviving canonical shell quartets (pair p >= pair q in kernel
+    order, Q_p*Q_q >= tau) as FUNCTION quartets: returns (function_quartets[int32, n x 4],
+    n_shell_quartets).  Every Cartesian component of a sampled shell quartet is included."""
+    rng = np.random.default_rng(seed)
+    npair = len(Q)
+    ncart = lambda l: (l + 1) * (l + 2) // 2
+    out, got = [], 0
+    while got < count:
+        p = rng.integers(0, npair, size=4 * count)
+        q = rng.integers(0, npair, size=4 * count)
+        keep = (q <= p) & (Q[p] * Q[q] >= tau)
+        for pp, qq in zip(p[keep], q[keep]):
+            fa = [shell_first[sa[pp]] + i for i in range(ncart(shell_l[sa[pp]]))]
+            fb = [shell_first[sb[pp]] + i for i in range(ncart(shell_l[sb[pp]]))]
+            fc = [shell_first[sa[qq]] + i for i in range(ncart(shell_l[sa[qq]]))]
+            fd = [shell_first[sb[qq]] + i for i in range(ncart(shell_l[sb[qq]]))]
+            out.extend((a, b, c, d) for a in fa for b in fb for c in fc for d in fd)
+            got += 1
+            if got >= count:
+                break
+    return np.array(out, dtype=np.int32), got
+
+
+def cpu_time_sample(orc, obasis, fq, n_shell, budget_s):
+    """Times the oracle (reference kernel when oracle/_ref is present) on the sampled
+    function quartets, repeating the whole sample until ~budget_s of wall time is used;
+    returns (shell_quartets/s, shell quartets evaluated, seconds)."""
+    t0 = time.perf_counter()
+    orc.eval_quartets(obasis, fq, want_values=False)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    repeats = int(max(1, min(1000, budget_s / dt)))
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        orc.eval_quartets(obasis, fq, want_values=False)
+    dt = time.perf_counter() - t0
+    return n_shell * repeats / dt, n_shell * repeats, dt
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+
+    z, x, basis_name, tau, desc = make_workload(args.workload)
+    obasis = orc.make_basis(z, x, basis_name)
+    kind = "port"
+    if orc.ref_lib() is not None:
+        orc.use_reference_kernel(True)
+        kind = "reference"
+    # pair list + Schwarz bounds on the CPU (exact Boys, like the product), by the oracle
+    shell_l, shell_first = [], []
+    i = 0
+    while i < obasis.n:
+        l = int(obasis.powers[i].sum())
+        shell_l.append(l)
+        shell_first.append(i)
+        i += (l + 1) * (l + 2) // 2
+    shell_l, shell_first = np.array(shell_l), np.array(shell_first)
+    ns = len(shell_l)
+    ii, jj = np.tril_indices(ns)
+    swap = shell_l[ii] < shell_l[jj]
+    sa, sb = np.where(swap, jj, ii), np.where(swap, ii, jj)
+    ncart = lambda l: (l + 1) * (l + 2) // 2
+    diag = []
+    owner = []
+    for p in range(len(sa)):
+        fa = [shell_first[sa[p]] + k for k in range(ncart(shell_l[sa[p]]))]
+        fb = [shell_first[sb[p]] + k for k in range(ncart(shell_l[sb[p]]))]
+        for a in fa:
+            for b in fb:
+                diag.append((a, b, a, b))
+                owner.append(p)
+    vals = orc.eval_quartets(obasis, np.array(diag, dtype=np.int32), orc.BOYS_EXACT)
+    Q = np.zeros(len(sa))
+    np.maximum.at(Q, np.array(owner), np.abs(vals))
+    Q = np.sqrt(Q)
+    cores = host_cores()
+    per_step = max(2.0, min(args.cpu_seconds, 60.0 / max(1, args.steps + args.warmup)))
+    fq, n_shell = sample_shell_quartets(shell_l, shell_first, sa, sb, Q, tau, 20000)
+    rates, times = [], []
+    for s in range(args.warmup + args.steps):
+        rate, used, dt = cpu_time_sample(orc, obasis, fq, n_shell, per_step)
+        if s >= args.warmup:
+            rates.append(rate)
+            times.append(dt)
+    value = float(np.mean(rates))
+    sample = (f"{n_shell} seeded random surviving shell quartets of the workload (all Cartesian "
+              f"components, all primitives) evaluated {used // n_shell}x per step; libpyquante2 "
+              f"coulomb_repulsion via basis.rs loop order, OpenMP x{cores}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "basis": basis_name, "schwarz_tau": tau,
+                   "nbf": int(obasis.n), "boys": "reference (libpyquante2 Fgamma)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import rchem_b200 as rc
+    from rchem_b200 import geometry as geo
+    from rchem_b200 import parallel
+
+    if rc.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (rchem_b200 has no CPU path)")
+    rank, world, local = parallel.init_distributed("nccl")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    z, x, basis_name, tau, desc = make_workload(args.workload)
+    basis = rc.Basis.new(z, x, basis_name)
+    basis.set_device(local)
+    basis.set_schwarz_tau(tau)
+    basis.set_boys(rc.BOYS_REFERENCE if args.boys == "reference" else rc.BOYS_EXACT)
+    n = basis.nbf
+    D_host = torch.from_numpy(geo.synthetic_density(n)).pin_memory()
+    D_dev = D_host.to(dev)
+    JK_dev = torch.zeros((2, n, n), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    basis.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        flush.fill_(1.0)
+        parallel.jk_direct_distributed(basis, D_dev, JK_dev, rank, world)
+
+    J_host = torch.empty((n, n), dtype=torch.float64).pin_memory()
+    K_host = torch.empty((n, n), dtype=torch.float64).pin_memory()
+    JK_host = torch.empty((2, n, n), dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        flush.fill_(1.0)
+        if world == 1:
+            # the reference-facing call: JK_direct(&mut J, &mut K, &basis, &D) with host buffers
+            rc.JK_direct(J_host.numpy(), K_host.numpy(), basis, D_host.numpy())
+        else:
+            d = D_host.to(dev, non_blocking=True)
+            parallel.jk_direct_distributed(basis, d, JK_dev, rank, world)
+            JK_host.copy_(JK_dev, non_blocking=True)
+            torch.cuda.synchronize()
+
+    # ---- warm-up (first call also builds pair data, Schwarz bounds and the task tables) ----
+    for _ in range(max(args.warmup, 1)):
+        step_resident()
+    barrier()
+    stats0 = basis.stats()
+
+    # ---- timed: device-resident -------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    kernel_ms = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        step_resident()
+        if rank == 0 and world == 1:
+            kernel_ms.append(basis.stats()["kernel_ms"])  # syncs on the library's end event
+    e1.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    ms_total = e0.elapsed_time(e1)
+    if world == 1 and not kernel_ms:
+        kernel_ms = [basis.stats()["kernel_ms"]]
+    # subtract nothing: the L2 flush (~0.1 ms) is part of the step
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+
+    # ---- timed: end to end through the host-buffer API ---------------------------------------
+    for _ in range(1):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record(stream)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clocks = sampler.stop()
+
+    # ---- whole-job counts ---------------------------------------------------------------------
+    st = basis.stats()
+    counts = torch.tensor([st["shell_quartets"], st["prim_quartets"], st["integrals"],
+                           st["model_flops"], st["launches"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    sq, pq, ints, flops, launches = [float(v) for v in counts.tolist()]
+    basis.use_own_stream()
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    ms_per_step = ms_total / args.steps
+    value = sq / (ms_per_step * 1e-3)
+    e2e_value = sq / (e2e_s / args.steps)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "basis": basis_name, "schwarz_tau": tau, "nbf": n,
+                   "boys": "reference (libpyquante2 Fgamma, 1e-12 parity)" if args.boys == "reference"
+                   else "exact (tabulated Taylor; <=2e-8 from libpyquante2)",
+                   "shell_quartets_per_step": sq, "shell_quartets_unscreened": st["shell_quartets_all"],
+                   "primitive_quartets_per_step": pq, "integrals_per_step": ints,
+                   "l2_flush": "256 MiB fill between steps",
+                   "parallelism": f"quartet blocks round-robin over {world} GPU(s) + 1 all-reduce of [J|K]"},
+        "integrals_per_s": ints / (ms_per_step * 1e-3),
+        "primitive_quartets_per_s": pq / (ms_per_step * 1e-3),
+        "jk_build_ms": ms_per_step,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n * n * world,
+                "d2h_bytes_per_step": 16 * n * n * (world if world > 1 else 1),
+                "ms_per_step": 1e3 * e2e_s / args.steps,
+                "api": "rchem_jk_direct (host buffers)" if world == 1 else
+                       "pinned D -> H2D -> rchem_jk_direct_device + all-reduce -> D2H"},
+        "gpu_launches": int(launches * args.steps),
+        "clocks": clocks,
+    }
+    # ---- roofline: FP64 pipe --------------------------------------------------------------------
+    peak_best, peak_avg = rc.fp64_peak(local, 10)
+    if world == 1:
+        k_ms = float(np.mean(kernel_ms))
+        achieved = flops / (k_ms * 1e-3) / 1e12
+    else:
+        k_ms = ms_per_step
+        achieved = flops / (k_ms * 1e-3) / 1e12 / world
+    line["roofline"] = {
+        "bound": "fp64", "achieved": achieved, "peak": peak_avg, "unit": "TFLOP/s",
+        "frac": achieved / peak_avg, "traffic": None,
+        "peak_source": "measured in this run: DFMA microbenchmark rchem_fp64_peak (avg of 10; "
+                       f"best {peak_best:.2f}); MEASURED_PEAKS.json has no FP64 entry",
+        "kernel": "eri_kernel<la,lb,lc,ld,boys,JK> (all class instantiations of one step)",
+        "kernel_ms_per_step": k_ms,
+        "algorithmic_flops_per_step": flops,
+        "flop_model": "SURVEY 8(d): sum over surviving quartets of K2_bra*K2_ket*P(class)+H(class)",
+        "per_gpu": world > 1,
+    }
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+
+        kind = "port"
+        if orc.ref_lib() is not None:
+            orc.use_reference_kernel(True)
+            kind = "reference"
+        obasis = orc.make_basis(z, x, basis_name)
+        sa, sb, _, Q = basis.schwarz()
+        l, first = basis.shells()
+        fq, n_shell = sample_shell_quartets(l, first, sa, sb, Q, tau, 20000)
+        rate, used, dt = cpu_time_sample(orc, obasis, fq, n_shell, args.cpu_seconds)
+        line["cpu_baseline"] = {
+            "value": rate, "unit": UNIT, "cores": host_cores(), "kind": kind,
+            "sample": f"{n_shell} seeded random surviving shell quartets of the workload, all "
+                      f"components and primitives, evaluated {used // n_shell}x ({dt:.1f} s); "
+                      "libpyquante2 coulomb_repulsion in basis.rs loop order, OpenMP"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -82,8 +82,11 @@ int64_t rchem_ijkl2intindex(int64_t i, int64_t j, int64_t k, int64_t l);
 #define RCHEM_OPT_DEVICE 3      /* CUDA device ordinal, before the first compute call          */
 int rchem_set_option(rchem_basis* b, int key, double value);
 double rchem_get_option(const rchem_basis* b, int key);
-/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = handle's own */
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream).  The value is used as
+ * is: NULL is the CUDA legacy default stream.  rchem_use_own_stream() goes back to the
+ * handle's private non-blocking stream (the initial state). */
 int rchem_set_stream(rchem_basis* b, void* cuda_stream);
+int rchem_use_own_stream(rchem_basis* b);
 
 /* ---------------- the hot path, HOST buffers (copies are inside the call) ------------- */
 
@@ -129,6 +132,10 @@ typedef struct {
   int32_t n_tasks;            /* batch pairs                                               */
 } rchem_stats;
 int rchem_get_stats(const rchem_basis* b, rchem_stats* out);
+
+/* Measured FP64-pipe peak of `device` (DFMA microbenchmark, TFLOP/s): best of `repeats`
+ * launches and the average over them.  The denominator of the FP64 roofline fraction. */
+int rchem_fp64_peak(int device, int repeats, double* tflops_best, double* tflops_sustained);
 
 /* ---------------- tier 1: symbol-compatible primitive integral ----------------------- */
 /* coulomb_repulsion with the exact libpyquante2 signature (cints.h:23-30), evaluated on the

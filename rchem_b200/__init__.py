@@ -79,6 +79,7 @@ _sig("rchem_ijkl2intindex", C.c_int64, [C.c_int64] * 4)
 _sig("rchem_set_option", C.c_int, [_vp, C.c_int, C.c_double])
 _sig("rchem_get_option", C.c_double, [_vp, C.c_int])
 _sig("rchem_set_stream", C.c_int, [_vp, _vp])
+_sig("rchem_use_own_stream", C.c_int, [_vp])
 _sig("rchem_build_I", C.c_int, [_vp, _dp])
 _sig("rchem_jk_direct", C.c_int, [_vp, _dp, _dp, _dp])
 _sig("rchem_jk_inmem", C.c_int, [C.c_int, _dp, _dp, _dp, _dp])
@@ -88,6 +89,7 @@ _sig("rchem_jk_inmem_device", C.c_int, [C.c_int, _vp, _vp, _vp, _vp])
 _sig("rchem_schwarz", C.c_int64, [_vp, _vp, _vp, _vp, _vp])
 _sig("rchem_quartet_list", C.c_int64, [_vp, _vp, C.c_int64])
 _sig("rchem_get_stats", C.c_int, [_vp, C.POINTER(Stats)])
+_sig("rchem_fp64_peak", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)])
 _sig("rchem_coulomb_repulsion_batch", C.c_int, [C.c_int64, _dp, _dp, _ip, _dp, C.c_int, _dp])
 _sig("coulomb_repulsion", C.c_double, ([C.c_double] * 4 + [C.c_int] * 3 + [C.c_double]) * 4)
 
@@ -100,6 +102,13 @@ def _check(rc):
 
 def device_count():
     return _lib.rchem_device_count()
+
+
+def fp64_peak(device=0, repeats=10):
+    """Measured FP64-pipe peak (TFLOP/s): (best launch, average over `repeats` launches)."""
+    best, avg = C.c_double(), C.c_double()
+    _check(_lib.rchem_fp64_peak(device, repeats, C.byref(best), C.byref(avg)))
+    return best.value, avg.value
 
 
 def get_ijk_list(m):
@@ -188,7 +197,12 @@ class Basis:
         _check(_lib.rchem_set_option(self._h, OPT_DEVICE, float(ordinal)))
 
     def set_stream(self, cuda_stream_ptr):
-        _check(_lib.rchem_set_stream(self._h, _vp(cuda_stream_ptr)))
+        """Run on this cudaStream_t (0/None = the legacy default stream, which is what
+        torch.cuda.current_stream().cuda_stream returns by default)."""
+        _check(_lib.rchem_set_stream(self._h, _vp(cuda_stream_ptr or None)))
+
+    def use_own_stream(self):
+        _check(_lib.rchem_use_own_stream(self._h))
 
     def stats(self):
         s = Stats()

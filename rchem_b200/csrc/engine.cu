@@ -152,6 +152,7 @@ struct rchem_basis {
   bool ready = false;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  bool external_stream = false;
   std::vector<Batch> batches;
   std::vector<TaskTable> tasks;
   double tasks_tau = -1.0;
@@ -240,7 +241,7 @@ int ensure_ready(rchem_basis* h) {
   if (h->shells.lmax > 2)
     return fail(RCHEM_ERR_UNSUPPORTED_AM, "class kernels cover s, p and d shells only");
   if (!h->own_stream) CUDA_OK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  if (!h->stream) h->stream = h->own_stream;
+  if (!h->external_stream) h->stream = h->own_stream;
   CUDA_OK(cudaEventCreate(&h->ev0));
   CUDA_OK(cudaEventCreate(&h->ev1));
 
@@ -578,7 +579,15 @@ double rchem_get_option(const rchem_basis* h, int key) {
 
 int rchem_set_stream(rchem_basis* h, void* s) {
   if (!h) return fail(RCHEM_ERR_INVALID_ARG, "null handle");
-  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  h->stream = (cudaStream_t)s;  // NULL == the legacy default stream
+  h->external_stream = true;
+  return RCHEM_OK;
+}
+
+int rchem_use_own_stream(rchem_basis* h) {
+  if (!h) return fail(RCHEM_ERR_INVALID_ARG, "null handle");
+  h->external_stream = false;
+  h->stream = h->own_stream;  // still null before the first compute call; set in ensure_ready
   return RCHEM_OK;
 }
 

@@ -1,0 +1,283 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against the
+oracle on identical inputs.  Tolerances: 1e-12 absolute per integral in fp64 (north star);
+bit-exact for the screened quartet list."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+RA, RB, RC_, RD = [1.0, 0.0, 1.0], [0.0, 1.0, 2.0], [0.0, 0.0, 3.0], [0.0, 0.0, 4.0]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(rc):
+    assert rc.device_count() >= 1, "GPU tests need a CUDA device (there is no CPU fallback)"
+
+
+# ---- tier 1: the libpyquante2 symbol ---------------------------------------------------------
+def test_tier1_reference_golden_values(rc):
+    # tho66.rs:288-321 (1e-12) through the pyquante2_coulomb_repulsion-shaped wrapper
+    v = rc.coulomb_repulsion(1.1, 1.2, 1.3, 1.4, RA, RB, RC_, RD, 1.0, 1.0, 1.0, 1.0, [0] * 12)
+    assert abs(v - 0.08608517834596989) < 1.0e-12
+    # os86.rs:882-937 known answers (exact Boys)
+    for pw, val in (([0] * 12, 0.08608517834596989), ([1] + [0] * 11, -0.046888060557776973),
+                    ([2, 1, 0, 1, 0, 0, 1, 0, 0, 0, 1, 0], 1.71817807954e-05)):
+        got = rc.coulomb_repulsion_batch([RA + RB + RC_ + RD], [[1.0] * 4], [pw],
+                                         [[1.1, 1.2, 1.3, 1.4]], rc.BOYS_EXACT)[0]
+        assert abs(got - val) < (1e-15 if abs(val) > 1e-3 else 1e-16)
+
+
+def test_tier1_batch_against_reference_fixture(rc):
+    g = golden("primitives_ref.npz")
+    got = rc.coulomb_repulsion_batch(g["centres"], g["norms"], g["powers"], g["alphas"])
+    assert np.abs(got - g["tho"]).max() < TOL
+    assert np.abs(got - g["tho"]).max() < 1e-13 * max(1.0, np.abs(g["tho"]).max())
+
+
+# ---- dense tensor (build_I) --------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["water_crawford", "water"])
+def test_build_I_water_sto3g_fixture(rc, tag):
+    # BASELINE.json configs 1 and 2
+    g = golden(f"{tag}_sto3g.npz")
+    b = rc.Basis.new(g["atomnos"], g["coords"], "STO-3G")
+    I = rc.build_I(b)
+    assert I.shape == (7, 7, 7, 7)
+    assert np.abs(I - g["I"]).max() < TOL
+    st = b.stats()
+    assert st["shell_quartets"] == 120 and st["launches"] >= 1  # 5 shells -> 15 pairs -> 120
+
+
+@pytest.mark.parametrize("basis_name", ["STO-3G", "6-31G", "6-31G*"])
+def test_build_I_all_classes_vs_oracle(rc, orc, geo, ref_or_restated, basis_name):
+    z, x = geo.molecule(geo.WATER_CRAWFORD)
+    b = rc.Basis.new(z, x, basis_name)
+    ob = orc.make_basis(z, x, basis_name)
+    with ref_or_restated():
+        I_ref = orc.build_I(ob)
+    I = rc.build_I(b)
+    assert np.abs(I - I_ref).max() < TOL
+    # all 8 index permutations are filled (basis.rs:451-454 plus the bra<->ket swap)
+    for perm in ((1, 0, 2, 3), (0, 1, 3, 2), (2, 3, 0, 1), (3, 2, 1, 0)):
+        assert np.array_equal(I, I.transpose(perm))
+    # exact-Boys flavour against the exact-Boys twin oracle
+    b.set_boys(rc.BOYS_EXACT)
+    I_x = rc.build_I(b)
+    assert np.abs(I_x - orc.build_I(ob, orc.BOYS_EXACT)).max() < TOL
+    assert np.abs(I_x - I_ref).max() < 2e-8  # Boys-limited, not a parity claim
+
+
+def test_d_shell_fixture(rc):
+    g = golden("water_crawford_631gs.npz")
+    b = rc.Basis.new(g["atomnos"], g["coords"], "6-31G*")
+    I = rc.build_I(b)
+    i = g["idx"]
+    assert np.abs(I[i[:, 0], i[:, 1], i[:, 2], i[:, 3]] - g["vals"]).max() < TOL
+    J, K = np.zeros((19, 19)), np.zeros((19, 19))
+    rc.JK_direct(J, K, b, g["D"])
+    assert np.abs(J - g["J"]).max() < TOL and np.abs(K - g["K"]).max() < TOL
+
+
+def test_multicentre_d_sample(rc):
+    g = golden("water2_631gs_sample.npz")
+    b = rc.Basis.new(g["atomnos"], g["coords"], "6-31G*")
+    I = rc.build_I(b)
+    i = g["idx"]
+    assert np.abs(I[i[:, 0], i[:, 1], i[:, 2], i[:, 3]] - g["vals"]).max() < TOL
+
+
+def test_build_I_from_explicit_cgtos(rc, orc, geo):
+    z, x = geo.water_cluster(2)
+    ob = orc.make_basis(z, x, "6-31G")
+    b = rc.Basis.from_cgtos(ob.origins, ob.powers, ob.prim_offset, ob.exps, ob.coefs, ob.norms)
+    I = rc.build_I(b)
+    q = np.random.default_rng(5).integers(0, ob.n, size=(2000, 4)).astype(np.int32)
+    assert np.abs(I[q[:, 0], q[:, 1], q[:, 2], q[:, 3]] - orc.eval_quartets(ob, q)).max() < TOL
+
+
+# ---- J/K --------------------------------------------------------------------------------------
+def test_jk_direct_water_fixture_and_oracle(rc, orc):
+    g = golden("water_crawford_sto3g.npz")
+    b = rc.Basis.new(g["atomnos"], g["coords"], "STO-3G")
+    J, K = np.full((7, 7), 99.0), np.full((7, 7), -99.0)  # must be overwritten (basis.rs:389-390)
+    rc.JK_direct(J, K, b, g["D"])
+    assert np.abs(J - g["J"]).max() < TOL and np.abs(K - g["K"]).max() < TOL
+    # the reference's own loop nest (no symmetry, 2 N^4 K^4 primitive calls)
+    Jo, Ko = orc.jk_direct(orc.make_basis(g["atomnos"], g["coords"], "STO-3G"), g["D"])
+    assert np.abs(J - Jo).max() < TOL and np.abs(K - Ko).max() < TOL
+    # repeated calls give the same answer (buffers are re-zeroed)
+    J2, K2 = np.zeros((7, 7)), np.zeros((7, 7))
+    rc.JK_direct(J2, K2, b, g["D"])
+    assert np.abs(J2 - J).max() < 1e-14 and np.abs(K2 - K).max() < 1e-14
+
+
+def test_jk_direct_cluster_vs_oracle_tensor(rc, orc, geo, ref_or_restated):
+    z, x = geo.water_cluster(3)
+    b = rc.Basis.new(z, x, "6-31G")
+    ob = orc.make_basis(z, x, "6-31G")
+    n = ob.n
+    with ref_or_restated():
+        I_ref = orc.build_I(ob)
+    D = geo.synthetic_density(n)
+    Jo, Ko = orc.jk_inmem(I_ref, D)
+    J, K = np.zeros((n, n)), np.zeros((n, n))
+    rc.JK_direct(J, K, b, D)
+    assert np.abs(J - Jo).max() < TOL and np.abs(K - Ko).max() < TOL
+    # JK_inmem on the GPU-built tensor
+    Jg, Kg = rc.JK_inmem(rc.build_I(b), D)
+    assert np.abs(Jg - Jo).max() < TOL and np.abs(Kg - Ko).max() < TOL
+
+
+def test_jk_inmem_fixture(rc):
+    g = golden("water_sto3g.npz")
+    J, K = rc.JK_inmem(g["I"], g["D"])
+    assert np.abs(J - g["J"]).max() < 1e-13 and np.abs(K - g["K"]).max() < 1e-13
+
+
+def test_asymmetric_density_is_rejected(rc, geo):
+    z, x = geo.molecule(geo.WATER)
+    b = rc.Basis.new(z, x, "STO-3G")
+    D = np.arange(49.0).reshape(7, 7)
+    with pytest.raises(rc.RchemError) as ei:
+        rc.JK_direct(np.zeros((7, 7)), np.zeros((7, 7)), b, D)
+    assert ei.value.code == -6
+
+
+# ---- screening: Schwarz bounds and the quartet list -----------------------------------------------
+def test_schwarz_bounds_and_quartet_list(rc, orc, geo):
+    z, x = geo.water_cluster(4)
+    b = rc.Basis.new(z, x, "6-31G*")
+    ob = orc.make_basis(z, x, "6-31G*")
+    sa, sb, batch, Q = b.schwarz()
+    l, first = b.shells()
+    ns = len(l)
+    assert len(Q) == ns * (ns + 1) // 2
+    assert np.all(l[sa] >= l[sb])
+    # Q = sqrt(max |(ab|ab)|) over the shell pair's components, exact Boys
+    rng = np.random.default_rng(2)
+    ncart = lambda m: (m + 1) * (m + 2) // 2
+    for p in rng.choice(len(Q), size=60, replace=False):
+        fa = [first[sa[p]] + i for i in range(ncart(l[sa[p]]))]
+        fb = [first[sb[p]] + i for i in range(ncart(l[sb[p]]))]
+        quartets = np.array([[i, j, i, j] for i in fa for j in fb], dtype=np.int32)
+        ref = np.sqrt(np.abs(orc.eval_quartets(ob, quartets, orc.BOYS_EXACT)).max())
+        assert abs(Q[p] - ref) < TOL
+    # inside a batch the pairs are sorted by Q, descending
+    for bt in np.unique(batch):
+        q = Q[batch == bt]
+        assert np.all(q[:-1] >= q[1:])
+    # the implicit list, materialised on the GPU, equals the CPU builder BIT-EXACTLY on the
+    # shared Q array
+    for tau in (0.0, 1e-10, 1e-6):
+        b.set_schwarz_tau(tau)
+        got = b.quartet_list()
+        offs = {bt: int(np.flatnonzero(batch == bt)[0]) for bt in np.unique(batch)}
+        exp = []
+        for bi in sorted(offs):
+            for ki in sorted(offs):
+                if ki > bi:
+                    continue
+                pq = orc.quartet_list(Q[batch == bi], Q[batch == ki], bi == ki, tau).astype(np.int64)
+                pq[:, 0] += offs[bi]
+                pq[:, 1] += offs[ki]
+                exp.append(pq)
+        exp = np.concatenate(exp)
+        assert got.shape == exp.shape and np.array_equal(got, exp)
+    npair = len(Q)
+    b.set_schwarz_tau(0.0)
+    assert len(b.quartet_list()) == npair * (npair + 1) // 2
+
+
+def test_screened_jk_error_is_bounded(rc, geo):
+    z, x = geo.water_cluster(8)
+    b = rc.Basis.new(z, x, "6-31G")
+    n = b.nbf
+    D = geo.synthetic_density(n)
+    J0, K0 = np.zeros((n, n)), np.zeros((n, n))
+    rc.JK_direct(J0, K0, b, D)
+    full = b.stats()["shell_quartets"]
+    b.set_schwarz_tau(1e-10)
+    J1, K1 = np.zeros((n, n)), np.zeros((n, n))
+    rc.JK_direct(J1, K1, b, D)
+    st = b.stats()
+    assert st["shell_quartets"] < full and st["shell_quartets_all"] == full
+    # every dropped integral is < tau in magnitude; |D| <= ~4/n
+    bound = 1e-10 * np.abs(D).sum() * 4
+    assert np.abs(J1 - J0).max() < bound and np.abs(K1 - K0).max() < bound
+
+
+# ---- size-independent properties at a BASELINE size ((H2O)_10 STO-3G, config 3) ----------------------
+def test_properties_water10(rc, orc, geo):
+    z, x = geo.water_cluster(10)
+    b = rc.Basis.new(z, x, "STO-3G")
+    ob = orc.make_basis(z, x, "STO-3G")
+    n = b.nbf
+    assert n == 70
+    D1 = geo.synthetic_density(n, seed=1)
+    D2 = geo.synthetic_density(n, seed=2)
+
+    def jk(D):
+        J, K = np.zeros((n, n)), np.zeros((n, n))
+        rc.JK_direct(J, K, b, D)
+        return J, K
+
+    J1, K1 = jk(D1)
+    J2, K2 = jk(D2)
+    J12, K12 = jk(D1 + 2.0 * D2)
+    assert np.abs(J12 - (J1 + 2 * J2)).max() < 1e-12 and np.abs(K12 - (K1 + 2 * K2)).max() < 1e-12
+    assert np.abs(J1 - J1.T).max() < 1e-13 and np.abs(K1 - K1.T).max() < 1e-13
+    # the Coulomb and exchange super-operators are symmetric: <D2|J[D1]> = <D1|J[D2]>
+    assert abs((J1 * D2).sum() - (J2 * D1).sum()) < 1e-12
+    assert abs((K1 * D2).sum() - (K2 * D1).sum()) < 1e-12
+    # spot-check against the oracle: J and K rows rebuilt from oracle integrals
+    rng = np.random.default_rng(0)
+    for mu, nu in rng.integers(0, n, size=(3, 2)):
+        qs = np.array([[mu, nu, la, si] for la in range(n) for si in range(n)], dtype=np.int32)
+        assert abs((orc.eval_quartets(ob, qs).reshape(n, n) * D1).sum() - J1[mu, nu]) < TOL
+        qs = np.array([[mu, la, nu, si] for la in range(n) for si in range(n)], dtype=np.int32)
+        assert abs((orc.eval_quartets(ob, qs).reshape(n, n) * D1).sum() - K1[mu, nu]) < TOL
+    # dense tensor (192 MB) vs direct J/K, and a sample of its elements vs the oracle
+    I = rc.build_I(b)
+    Jm, Km = rc.JK_inmem(I, D1)
+    assert np.abs(Jm - J1).max() < 1e-12 and np.abs(Km - K1).max() < 1e-12
+    q = rng.integers(0, n, size=(4000, 4)).astype(np.int32)
+    assert np.abs(I[q[:, 0], q[:, 1], q[:, 2], q[:, 3]] - orc.eval_quartets(ob, q)).max() < TOL
+
+
+# ---- device-buffer API and the multi-GPU partition -----------------------------------------------------
+def test_device_api_and_rank_partition(rc, geo):
+    torch = pytest.importorskip("torch")
+    from rchem_b200 import parallel
+
+    z, x = geo.water_cluster(5)
+    b = rc.Basis.new(z, x, "6-31G*")
+    n = b.nbf
+    D = geo.synthetic_density(n)
+    J, K = np.zeros((n, n)), np.zeros((n, n))
+    rc.JK_direct(J, K, b, D)
+    dev = torch.device("cuda", 0)
+    Dd = torch.from_numpy(D).to(dev)
+    b.set_stream(torch.cuda.current_stream().cuda_stream)
+    total = torch.zeros((2, n, n), dtype=torch.float64, device=dev)
+    quartets = 0
+    for rank in range(3):  # three "ranks" on one GPU: shares must add up to the whole
+        part = torch.empty((2, n, n), dtype=torch.float64, device=dev)
+        parallel.jk_direct_distributed(b, Dd, part, rank, 3)
+        total += part
+        quartets += b.stats()["shell_quartets"]
+    torch.cuda.synchronize()
+    assert abs(quartets - b.stats()["shell_quartets_all"]) <= 3 * b.stats()["n_tasks"]
+    assert np.abs(total[0].cpu().numpy() - J).max() < 1e-12
+    assert np.abs(total[1].cpu().numpy() - K).max() < 1e-12
+    # dense tensor on a device buffer + JK_inmem on device buffers
+    I = torch.empty((n,) * 4, dtype=torch.float64, device=dev)
+    b.build_I_device(I.data_ptr())
+    JK = torch.empty((2, n, n), dtype=torch.float64, device=dev)
+    rc.jk_inmem_device(n, I.data_ptr(), Dd.data_ptr(), JK.data_ptr(),
+                       torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.abs(JK[0].cpu().numpy() - J).max() < 1e-12
+    assert np.abs(JK[1].cpu().numpy() - K).max() < 1e-12
+    b.use_own_stream()

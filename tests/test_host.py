@@ -1,0 +1,234 @@
+"""CPU tests of the host logic: C-ABI surface, data model, the generated recurrences (through
+the test-only host build), the Boys restatement, error behaviour without a GPU, and the
+world_size-2 gloo path of the J/K all-reduce."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+
+
+def test_abi_exports_every_declared_symbol(rc):
+    hdr = open(os.path.join(ROOT, "include", "rchem_eri.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(rchem_[a-z_0-9A-Z]+|coulomb_repulsion)\s*\(", hdr))
+    assert {"rchem_build_I", "rchem_jk_direct", "rchem_jk_inmem", "coulomb_repulsion",
+            "rchem_basis_new", "rchem_schwarz", "rchem_quartet_list"} <= names
+    out = subprocess.run(["nm", "-D", "--defined-only", rc.LIB_PATH], capture_output=True,
+                         text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = names - exported
+    assert not missing, f"declared in include/rchem_eri.h but not exported: {missing}"
+    assert rc._lib.rchem_version() >= 100
+
+
+def test_library_has_sm100a_code(rc):
+    out = subprocess.run(["cuobjdump", "-lelf", rc.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+
+
+@pytest.mark.parametrize("name,nbf,nshell", [("STO-3G", 7, 5), ("6-31G", 13, 9), ("6-31G*", 19, 10)])
+def test_basis_new_matches_oracle_statement(rc, orc, geo, name, nbf, nshell):
+    z, x = geo.molecule(geo.WATER_CRAWFORD)
+    b = rc.Basis.new(z, x, name)
+    ob = orc.make_basis(z, x, name)
+    assert len(b) == nbf == ob.n
+    origins, powers, off, exps, coefs, norms = b.export()
+    assert np.array_equal(origins, ob.origins) and np.array_equal(powers, ob.powers)
+    assert np.array_equal(off, ob.prim_offset) and np.array_equal(exps, ob.exps)
+    assert np.array_equal(coefs, ob.coefs)
+    assert np.abs(norms / ob.norms - 1).max() < 4e-16
+    l, first = b.shells()
+    assert len(l) == nshell
+    # function order atom -> shell -> am -> component (basis.rs:186-203): O first, then H, H
+    assert np.allclose(origins[0], x[0]) and np.allclose(origins[-1], x[2])
+
+
+def test_basis_from_cgtos_roundtrip_and_layout_errors(rc, orc, geo):
+    z, x = geo.molecule(geo.WATER_CRAWFORD)
+    ob = orc.make_basis(z, x, "6-31G*")
+    b = rc.Basis.from_cgtos(ob.origins, ob.powers, ob.prim_offset, ob.exps, ob.coefs, ob.norms)
+    assert len(b) == 19
+    # drop one p component: no longer complete Cartesian shells
+    keep = [i for i in range(ob.n) if i != 3]
+    off = [0]
+    ex, co, no = [], [], []
+    for i in keep:
+        s, e = ob.prim_offset[i], ob.prim_offset[i + 1]
+        ex += list(ob.exps[s:e]); co += list(ob.coefs[s:e]); no += list(ob.norms[s:e])
+        off.append(len(ex))
+    with pytest.raises(rc.RchemError) as ei:
+        rc.Basis.from_cgtos(ob.origins[keep], ob.powers[keep], off, ex, co, no)
+    assert ei.value.code == -3
+    with pytest.raises(rc.RchemError) as ei:
+        rc.Basis.new(z, x, "cc-pVQZ")
+    assert ei.value.code == -8
+    with pytest.raises(rc.RchemError):
+        rc.Basis.new(np.array([8, 1, 79], dtype=np.uint64), x, "STO-3G")
+
+
+def test_helpers_match_reference_semantics(rc, orc):
+    assert rc.get_ijk_list(3).tolist() == orc.ijk_list(3).tolist()  # shell.rs:44-61
+    for pw, a in (([0, 0, 0], 1.3), ([1, 0, 0], 0.4), ([1, 1, 0], 0.8), ([2, 0, 0], 0.8), ([0, 1, 2], 5.0)):
+        ref = orc.lib().orc_normalization(np.array(pw, dtype=np.int32), a)
+        assert abs(rc.normalization(pw, a) / ref - 1) < 4e-16
+    g = golden("ijkl_ref.npz")
+    assert [rc.ijkl2intindex(*map(int, q)) for q in g["ijkl"]] == g["index"].tolist()
+
+
+def test_no_cpu_fallback(rc, geo):
+    if rc.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    z, x = geo.molecule(geo.WATER_CRAWFORD)
+    b = rc.Basis.new(z, x, "STO-3G")
+    J, K = np.zeros((7, 7)), np.zeros((7, 7))
+    with pytest.raises(rc.RchemError) as ei:
+        rc.JK_direct(J, K, b, np.eye(7))
+    assert ei.value.code == -5
+    with pytest.raises(rc.RchemError):
+        rc.build_I(b)
+    with pytest.raises(rc.RchemError):
+        rc.JK_inmem(np.zeros((2, 2, 2, 2)), np.eye(2))
+    with pytest.raises(rc.RchemError):
+        rc.coulomb_repulsion(1.1, 1.2, 1.3, 1.4, [1, 0, 1], [0, 1, 2], [0, 0, 3], [0, 0, 4], 1, 1, 1, 1, [0] * 12)
+
+
+def test_argument_validation(rc, geo):
+    z, x = geo.molecule(geo.WATER_CRAWFORD)
+    b = rc.Basis.new(z, x, "STO-3G")
+    A = np.arange(49, dtype=np.float64).reshape(7, 7)
+    J, K = np.zeros((7, 7)), np.zeros((7, 7))
+    with pytest.raises(rc.RchemError) as ei:  # asymmetric D is rejected before any GPU work
+        rc.JK_direct(J, K, b, A)
+    assert ei.value.code == -6
+    with pytest.raises(ValueError):
+        rc.JK_direct(np.zeros((6, 6)), K, b, np.eye(7))
+    with pytest.raises(rc.RchemError):
+        b.set_boys(3)
+    with pytest.raises(rc.RchemError):
+        b.set_schwarz_tau(-1.0)
+    with pytest.raises(rc.RchemError) as ei:  # g function: tier-1 kernel stops at f
+        rc.coulomb_repulsion_batch(np.zeros((1, 12)), np.ones((1, 4)),
+                                   np.array([[4, 0, 0] + [0] * 9]), np.ones((1, 4)))
+    assert ei.value.code == -2
+
+
+# ---- the generated recurrences, on the host -----------------------------------------------
+def _shell_blocks(hostcheck, ob, boys, I_ref):
+    ls = np.zeros(ob.n, dtype=np.int32)
+    bf = np.zeros(ob.n, dtype=np.int32)
+    ns = hostcheck.hostcheck_nshells(*ob.args(), ls, bf)
+    nc = lambda l: (l + 1) * (l + 2) // 2
+    worst, classes = 0.0, set()
+    out = np.zeros(1296)
+    for sa in range(ns):
+        for sb in range(ns):
+            if ls[sa] < ls[sb]:
+                continue
+            for sc in range(ns):
+                for sd in range(ns):
+                    if ls[sc] < ls[sd] or (ls[sa], ls[sb]) < (ls[sc], ls[sd]):
+                        continue
+                    n = hostcheck.hostcheck_shell_quartet(*ob.args(), sa, sb, sc, sd, boys, out)
+                    assert n > 0
+                    blk = I_ref[bf[sa]:bf[sa] + nc(ls[sa]), bf[sb]:bf[sb] + nc(ls[sb]),
+                                bf[sc]:bf[sc] + nc(ls[sc]), bf[sd]:bf[sd] + nc(ls[sd])]
+                    worst = max(worst, np.abs(out[:n].reshape(blk.shape) - blk).max())
+                    classes.add((ls[sa], ls[sb], ls[sc], ls[sd]))
+    return worst, classes
+
+
+def test_all_21_classes_against_oracle(hostcheck, orc, geo, ref_or_restated):
+    z, x = geo.molecule(geo.WATER_CRAWFORD)
+    ob = orc.make_basis(z, x, "6-31G*")
+    with ref_or_restated():
+        I_ref = orc.build_I(ob)
+    worst, classes = _shell_blocks(hostcheck, ob, 0, I_ref)
+    assert len(classes) == 21
+    assert worst < 1e-12, worst  # reference Boys: the north-star tolerance
+    I_x = orc.build_I(ob, orc.BOYS_EXACT)
+    worst, _ = _shell_blocks(hostcheck, ob, 1, I_x)
+    assert worst < 1e-13, worst  # exact Boys vs the exact-Boys twin
+    assert 1e-9 < np.abs(I_x - I_ref).max() < 2e-8  # the two flavours differ by the Boys error
+
+
+def test_boys_reference_restatement_bitwise_iterations(hostcheck, orc):
+    g = golden("fgamma_ref.npz")
+    F = np.zeros(9)
+    worst = 0.0
+    for j, x in enumerate(g["x"]):
+        hostcheck.hostcheck_boys(0, 8, float(x), F)
+        ref = g["F"][:9, j]
+        worst = max(worst, np.abs(F / ref - 1).max())
+    # same loops, same iteration counts; only the smooth wrapper differs: the reference forms
+    # exp(-x + a ln x - lgamma a) whose argument carries ~|arg| ulp of rounding noise
+    assert worst < 1e-13, worst
+
+
+def test_boys_exact_table(hostcheck, orc):
+    L = orc.lib()
+    F = np.zeros(9)
+    worst = 0.0
+    for x in np.concatenate([np.linspace(0, 40, 997), [35.99, 36.0, 36.01, 1e-9, 200.0]]):
+        hostcheck.hostcheck_boys(1, 8, float(x), F)
+        ref = np.array([L.orc_fgamma_exact(float(m), float(x)) for m in range(9)])
+        worst = max(worst, np.abs(F / ref - 1).max())
+    assert worst < 5e-15, worst
+
+
+def test_flop_model_is_generated(rc):
+    import json
+
+    fl = json.load(open(os.path.join(ROOT, "rchem_b200", "csrc", "gen", "flops.json")))
+    assert len(fl) == 21
+    assert fl["1111"]["hrr_flops"] == 324 and fl["2222"]["hrr_flops"] == 10586
+    assert fl["1010"]["vrr_flops"] == 60
+
+
+# ---- multi-process host path (gloo, world_size 2) -------------------------------------------
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from rchem_b200 import parallel, geometry as geo
+from oracle import oracle as orc
+rank, world, _ = parallel.init_distributed("gloo")
+z, x = geo.molecule(geo.WATER_CRAWFORD)
+ob = orc.make_basis(z, x, "STO-3G")
+n = ob.n
+D = geo.synthetic_density(n)
+I = orc.build_I(ob)
+# each rank digests the (mu,nu) rows it owns, like the block-interleaved GPU partition
+JK = np.zeros((2, n, n))
+for row in range(n * n):
+    if parallel.block_owner(row, world) != rank:
+        continue
+    mu, nu = divmod(row, n)
+    JK[0, mu, nu] = (I[mu, nu] * D).sum()
+    JK[1, mu, nu] = (I[mu, :, nu, :] * D).sum()
+t = torch.from_numpy(JK)
+parallel.allreduce_jk(t)
+J, K = orc.jk_inmem(I, D)
+assert np.abs(t[0].numpy() - J).max() < 1e-13 and np.abs(t[1].numpy() - K).max() < 1e-13
+assert sum(parallel.blocks_of_rank(1001, r, world) for r in range(world)) == 1001
+dist.barrier()
+if rank == 0:
+    print("GLOO_OK")
+"""
+
+
+def test_gloo_world_size_2_allreduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                          "29611", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GLOO_OK" in out.stdout
