@@ -25,8 +25,10 @@
 namespace rchem {
 
 // launchers, one per class translation unit
-#define X(la, lb, lc, ld, tag) \
-  cudaError_t launch_eri_##tag(int, int, const EriTask&, unsigned, cudaStream_t);
+#define X(la, lb, lc, ld, tag)                                                        \
+  cudaError_t launch_eri_##tag(int, int, const EriTask&, unsigned, cudaStream_t);     \
+  cudaError_t launch_eri_block_##tag(int, const EriTask&, unsigned, size_t, cudaStream_t); \
+  EriBlockInfo block_info_##tag();
 RCHEM_ERI_CLASSES(X)
 #undef X
 
@@ -67,6 +69,18 @@ static EriLaunchFn find_launcher(int la, int lb, int lc, int ld) {
 #undef X
   return nullptr;
 }
+static EriBlockLaunchFn find_block_launcher(int la, int lb, int lc, int ld, EriBlockInfo* info) {
+#define X(a, b, c, d, tag)                                  \
+  if (la == a && lb == b && lc == c && ld == d) {           \
+    *info = block_info_##tag();                             \
+    return launch_eri_block_##tag;                          \
+  }
+  RCHEM_ERI_CLASSES(X)
+#undef X
+  return nullptr;
+}
+// dynamic shared memory the block kernel may use (227 KB per CTA on sm_100, minus slack)
+static constexpr size_t kMaxBlockSmem = 220 * 1024;
 
 struct Batch {
   int la = 0, lb = 0, K2 = 0, npairs = 0, stride = 0;
@@ -75,27 +89,64 @@ struct Batch {
   double* d_prim = nullptr;
   double* d_geom = nullptr;
   int* d_idx = nullptr;
-  BatchView view() const { return BatchView{d_prim, d_geom, d_idx, npairs, stride, K2}; }
+  double* d_Dp = nullptr;  // [ncart(la)*ncart(lb)][stride] packed D blocks
+  double* d_Jp = nullptr;  // [ncart(la)*ncart(lb)][stride] packed J blocks
+  int ncomp() const { return ncart(la) * ncart(lb); }
+  BatchView view() const { return BatchView{d_prim, d_geom, d_idx, d_Dp, d_Jp, npairs, stride, K2}; }
 };
 
 struct TaskTable {
   int bra = 0, ket = 0;
   long long nwarps = 0, nquartets = 0, nquartets_all = 0;
-  long long* d_prefix = nullptr;
+  long long* d_prefix = nullptr;  // warp chunks, every bra pair (tensor mode)
   int* d_nq = nullptr;
   std::vector<long long> h_prefix;  // kept for rchem_quartet_list
   std::vector<int> h_nq;
+  // J/K split: heavy bra pairs -> block kernel, light ones -> warp kernel
+  long long nwarps_light = 0, nquartets_light = 0, nblocks_heavy = 0;
+  int nheavy = 0;
+  long long* d_prefix_light = nullptr;
+  int* d_nq_light = nullptr;
+  int* d_hp = nullptr;
+  long long* d_hblk_prefix = nullptr;
+  size_t smem_bytes = 0;
 };
 
-__global__ void finalize_jk_kernel(const double* __restrict__ Jh, const double* __restrict__ Kh,
-                                   double* __restrict__ JK, int N) {
-  // J = Jh + Jh^T, K = Kh + Kh^T  (the two transposed halves of the 8-fold digestion)
+// D blocks of every shell pair of a batch, pair-major packed: Dp[ab][p] = D[bfA+a][bfB+b]
+__global__ void pack_d_kernel(const double* __restrict__ D, int N, const int* __restrict__ idx,
+                              int npairs, int stride, int nb, int ncomp, double* __restrict__ Dp) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  const int bfA = idx[p], bfB = idx[stride + p];
+  for (int c = 0; c < ncomp; ++c)
+    Dp[(size_t)c * stride + p] = D[(size_t)(bfA + c / nb) * N + bfB + c % nb];
+}
+
+// J from the packed pair blocks.  Every unordered function pair belongs to exactly one shell
+// pair, so this is a plain (non-atomic) scatter: J[i][j] = J[j][i] = Jp[ab] (+ Jp[ba] on a
+// diagonal shell pair, whose block holds both orders) -- i.e. J = Jh + Jh^T of the digestion.
+__global__ void finalize_j_kernel(const double* __restrict__ Jp, const int* __restrict__ idx,
+                                  int npairs, int stride, int nb, int ncomp, int N,
+                                  double* __restrict__ J) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  const int bfA = idx[p], bfB = idx[stride + p], diag = idx[2 * stride + p];
+  for (int c = 0; c < ncomp; ++c) {
+    const int a = c / nb, b = c % nb;
+    double v = Jp[(size_t)c * stride + p];
+    if (diag) v += Jp[(size_t)(b * nb + a) * stride + p];
+    J[(size_t)(bfA + a) * N + bfB + b] = v;
+    if (!diag) J[(size_t)(bfB + b) * N + bfA + a] = v;
+  }
+}
+
+__global__ void finalize_k_kernel(const double* __restrict__ Kh, double* __restrict__ K, int N) {
+  // K = Kh + Kh^T  (the two transposed halves of the 8-fold digestion)
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nn = (size_t)N * N;
   if (idx >= nn) return;
   const size_t i = idx / N, j = idx % N;
-  JK[idx] = Jh[idx] + Jh[j * N + i];
-  JK[nn + idx] = Kh[idx] + Kh[j * N + i];
+  K[idx] = Kh[idx] + Kh[j * N + i];
 }
 
 // JK_inmem (basis.rs:462-484) in ONE pass over the tensor: element I[i][j][k][l] feeds
@@ -157,7 +208,7 @@ struct rchem_basis {
   std::vector<TaskTable> tasks;
   double tasks_tau = -1.0;
   double* d_boys = nullptr;
-  double *d_D = nullptr, *d_Jh = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
+  double *d_D = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   rchem_stats stats{};
 };
@@ -208,6 +259,9 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
     CUDA_OK(cudaMalloc(&bt.d_prim, prim.size() * sizeof(double)));
     CUDA_OK(cudaMalloc(&bt.d_geom, geom.size() * sizeof(double)));
     CUDA_OK(cudaMalloc(&bt.d_idx, idx.size() * sizeof(int)));
+    CUDA_OK(cudaMalloc(&bt.d_Dp, (size_t)bt.ncomp() * st * sizeof(double)));
+    CUDA_OK(cudaMalloc(&bt.d_Jp, (size_t)bt.ncomp() * st * sizeof(double)));
+    CUDA_OK(cudaMemset(bt.d_Dp, 0, (size_t)bt.ncomp() * st * sizeof(double)));
   }
   CUDA_OK(cudaMemcpyAsync(bt.d_prim, prim.data(), prim.size() * sizeof(double),
                           cudaMemcpyHostToDevice, h->stream));
@@ -247,7 +301,7 @@ int ensure_ready(rchem_basis* h) {
 
   // exact-Boys grid
   std::vector<double> table;
-  build_boys_table(&table);
+  build_boys_tables(&table);
   CUDA_OK(cudaMalloc(&h->d_boys, table.size() * sizeof(double)));
   CUDA_OK(cudaMemcpy(h->d_boys, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
 
@@ -282,6 +336,7 @@ int ensure_ready(rchem_basis* h) {
     EriTask t;
     fill_common(h, &t);
     t.bra = t.ket = bt.view();
+    t.boys_table = h->d_boys + (size_t)(2 * (bt.la + bt.lb)) * kBoysTableLen;
     t.nwarps = (bt.npairs + 31) / 32;
     t.same = 1;
     t.Qout = dQ;
@@ -302,8 +357,7 @@ int ensure_ready(rchem_basis* h) {
 
   const size_t nn = (size_t)h->N * h->N;
   CUDA_OK(cudaMalloc(&h->d_D, nn * sizeof(double)));
-  CUDA_OK(cudaMalloc(&h->d_Jh, 2 * nn * sizeof(double)));
-  h->d_Kh = h->d_Jh + nn;
+  CUDA_OK(cudaMalloc(&h->d_Kh, nn * sizeof(double)));
   CUDA_OK(cudaMalloc(&h->d_JK, 2 * nn * sizeof(double)));
   h->ready = true;
   return RCHEM_OK;
@@ -313,6 +367,10 @@ void free_tasks(rchem_basis* h) {
   for (TaskTable& t : h->tasks) {
     if (t.d_prefix) cudaFree(t.d_prefix);
     if (t.d_nq) cudaFree(t.d_nq);
+    if (t.d_prefix_light) cudaFree(t.d_prefix_light);
+    if (t.d_nq_light) cudaFree(t.d_nq_light);
+    if (t.d_hp) cudaFree(t.d_hp);
+    if (t.d_hblk_prefix) cudaFree(t.d_hblk_prefix);
   }
   h->tasks.clear();
   h->tasks_tau = -1.0;
@@ -350,6 +408,38 @@ int ensure_tasks(rchem_basis* h) {
         tt.nquartets_all += full;
       }
       tt.nwarps = tt.h_prefix[B.npairs];
+      // J/K split.  Heavy: at least one full pass of the block kernel's threads, and the
+      // D/K rows of the bra functions fit in shared memory.
+      EriBlockInfo info{0, 0};
+      find_block_launcher(B.la, B.lb, K.la, K.lb, &info);
+      tt.smem_bytes = (size_t)2 * (ncart(B.la) + ncart(B.lb)) * h->N * sizeof(double) +
+                      (size_t)B.K2 * sizeof(PrimPair);
+      const bool rows_fit = tt.smem_bytes <= kMaxBlockSmem && info.threads > 0;
+      std::vector<int> nq_light(B.npairs), hp;
+      std::vector<long long> prefix_light(B.npairs + 1, 0), hblk(1, 0);
+      for (int p = 0; p < B.npairs; ++p) {
+        const int cut = tt.h_nq[p];
+        const bool heavy = rows_fit && cut >= info.threads;
+        nq_light[p] = heavy ? 0 : cut;
+        prefix_light[p + 1] = prefix_light[p] + (nq_light[p] + 31) / 32;
+        if (heavy) {
+          hp.push_back(p);
+          hblk.push_back(hblk.back() + (cut + info.kets_per_block - 1) / info.kets_per_block);
+        } else {
+          tt.nquartets_light += cut;
+        }
+      }
+      tt.nwarps_light = prefix_light[B.npairs];
+      tt.nheavy = (int)hp.size();
+      tt.nblocks_heavy = hblk.back();
+      CUDA_OK(cudaMalloc(&tt.d_prefix_light, prefix_light.size() * sizeof(long long)));
+      CUDA_OK(cudaMalloc(&tt.d_nq_light, std::max<size_t>(1, nq_light.size()) * sizeof(int)));
+      CUDA_OK(cudaMalloc(&tt.d_hp, std::max<size_t>(1, hp.size()) * sizeof(int)));
+      CUDA_OK(cudaMalloc(&tt.d_hblk_prefix, hblk.size() * sizeof(long long)));
+      CUDA_OK(cudaMemcpy(tt.d_prefix_light, prefix_light.data(), prefix_light.size() * sizeof(long long), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(tt.d_nq_light, nq_light.data(), nq_light.size() * sizeof(int), cudaMemcpyHostToDevice));
+      if (!hp.empty()) CUDA_OK(cudaMemcpy(tt.d_hp, hp.data(), hp.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(tt.d_hblk_prefix, hblk.data(), hblk.size() * sizeof(long long), cudaMemcpyHostToDevice));
       CUDA_OK(cudaMalloc(&tt.d_prefix, tt.h_prefix.size() * sizeof(long long)));
       CUDA_OK(cudaMalloc(&tt.d_nq, std::max<size_t>(1, tt.h_nq.size()) * sizeof(int)));
       CUDA_OK(cudaMemcpy(tt.d_prefix, tt.h_prefix.data(), tt.h_prefix.size() * sizeof(long long),
@@ -375,28 +465,55 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
     EriTask t = proto;
     t.bra = B.view();
     t.ket = K.view();
-    t.warp_prefix = tt.d_prefix;
+    t.boys_table = h->d_boys + (size_t)(B.la + B.lb + K.la + K.lb) * kBoysTableLen;
     t.nq = tt.d_nq;
-    t.nwarps = tt.nwarps;
     t.same = tt.bra == tt.ket;
     t.rank = rank;
     t.nranks = nranks;
-    const long long nblocks = (tt.nwarps + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const long long mine = nblocks > rank ? (nblocks - rank + nranks - 1) / nranks : 0;
-    if (mine > 0x7fffffffLL) return fail(RCHEM_ERR_TOO_LARGE, "task exceeds the grid limit");
     EriLaunchFn fn = find_launcher(B.la, B.lb, K.la, K.lb);
     if (!fn) return fail(RCHEM_ERR_UNSUPPORTED_AM, "no kernel for this class");
-    CUDA_OK(fn(h->boys, mode, t, (unsigned)mine, h->stream));
-    if (mine > 0) st.launches += 1;
-    // statistics (the share of this rank is the block-interleaved 1/nranks slice)
-    const double share = nblocks ? (double)mine / (double)nblocks : 0.0;
-    const long long q = (long long)std::llround(tt.nquartets * share);
     const FlopModel* fm = flop_model(B.la, B.lb, K.la, K.lb);
     const double k4 = (double)B.K2 * K.K2;
-    st.shell_quartets += q;
-    st.prim_quartets += (long long)(q * k4);
-    st.integrals += q * (long long)(ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb));
-    if (fm) st.model_flops += q * (k4 * fm->P + fm->H);
+    auto account = [&](double quartets) {
+      const long long q = (long long)std::llround(quartets);
+      st.shell_quartets += q;
+      st.prim_quartets += (long long)(q * k4);
+      st.integrals += q * (long long)(ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb));
+      if (fm) st.model_flops += q * (k4 * fm->P + fm->H);
+    };
+    // the share of this rank is the block-interleaved 1/nranks slice
+    auto my_blocks = [&](long long nblocks) {
+      return nblocks > rank ? (nblocks - rank + nranks - 1) / nranks : 0LL;
+    };
+    const bool split = mode == kModeJK;
+    // --- warp kernel (everything in tensor mode; the light bra pairs in J/K mode) ---
+    const long long nwarps = split ? tt.nwarps_light : tt.nwarps;
+    if (nwarps > 0) {
+      t.warp_prefix = split ? tt.d_prefix_light : tt.d_prefix;
+      t.nq = split ? tt.d_nq_light : tt.d_nq;
+      t.nwarps = nwarps;
+      const long long nblocks = (nwarps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+      const long long mine = my_blocks(nblocks);
+      if (mine > 0x7fffffffLL) return fail(RCHEM_ERR_TOO_LARGE, "task exceeds the grid limit");
+      CUDA_OK(fn(h->boys, mode, t, (unsigned)mine, h->stream));
+      if (mine > 0) st.launches += 1;
+      account((split ? tt.nquartets_light : tt.nquartets) * (double)mine / (double)nblocks);
+    }
+    // --- block kernel (heavy bra pairs, J/K mode) ---
+    if (split && tt.nblocks_heavy > 0) {
+      EriBlockInfo info{0, 0};
+      EriBlockLaunchFn bfn = find_block_launcher(B.la, B.lb, K.la, K.lb, &info);
+      t.nq = tt.d_nq;
+      t.hp = tt.d_hp;
+      t.hblk_prefix = tt.d_hblk_prefix;
+      t.nheavy = tt.nheavy;
+      t.nblocks_heavy = tt.nblocks_heavy;
+      const long long mine = my_blocks(tt.nblocks_heavy);
+      if (mine > 0x7fffffffLL) return fail(RCHEM_ERR_TOO_LARGE, "task exceeds the grid limit");
+      CUDA_OK(bfn(h->boys, t, (unsigned)mine, tt.smem_bytes, h->stream));
+      if (mine > 0) st.launches += 1;
+      account((tt.nquartets - tt.nquartets_light) * (double)mine / (double)tt.nblocks_heavy);
+    }
   }
   CUDA_OK(cudaEventRecord(h->ev1, h->stream));
   return RCHEM_OK;
@@ -480,9 +597,9 @@ void rchem_basis_destroy(rchem_basis* h) {
     cudaSetDevice(h->device);
     free_tasks(h);
     for (Batch& bt : h->batches) {
-      cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_idx);
+      cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_idx); cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
     }
-    cudaFree(h->d_boys); cudaFree(h->d_D); cudaFree(h->d_Jh); cudaFree(h->d_JK);
+    cudaFree(h->d_boys); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
   }
@@ -614,18 +731,27 @@ int rchem_jk_direct_device(rchem_basis* h, const double* D_dev, double* JK_dev, 
   rc = ensure_tasks(h);
   if (rc) return rc;
   const size_t nn = (size_t)h->N * h->N;
-  CUDA_OK(cudaMemsetAsync(h->d_Jh, 0, 2 * nn * sizeof(double), h->stream));  // J.fill(0); K.fill(0)
+  const int N = h->N;
+  // J.fill(0); K.fill(0) (basis.rs:389-390): the packed J blocks and the K half-accumulator
+  CUDA_OK(cudaMemsetAsync(h->d_Kh, 0, nn * sizeof(double), h->stream));
+  for (const Batch& bt : h->batches) {
+    CUDA_OK(cudaMemsetAsync(bt.d_Jp, 0, (size_t)bt.ncomp() * bt.stride * sizeof(double), h->stream));
+    pack_d_kernel<<<(bt.npairs + 255) / 256, 256, 0, h->stream>>>(
+        D_dev, N, bt.d_idx, bt.npairs, bt.stride, ncart(bt.lb), bt.ncomp(), bt.d_Dp);
+  }
+  CUDA_OK(cudaGetLastError());
   EriTask proto;
   fill_common(h, &proto);
   proto.D = D_dev;
-  proto.Jh = h->d_Jh;
   proto.Kh = h->d_Kh;
   rc = run_tasks(h, kModeJK, proto, rank, nranks);
   if (rc) return rc;
-  const unsigned grid = (unsigned)((nn + 255) / 256);
-  finalize_jk_kernel<<<grid, 256, 0, h->stream>>>(h->d_Jh, h->d_Kh, JK_dev, h->N);
+  for (const Batch& bt : h->batches)
+    finalize_j_kernel<<<(bt.npairs + 255) / 256, 256, 0, h->stream>>>(
+        bt.d_Jp, bt.d_idx, bt.npairs, bt.stride, ncart(bt.lb), bt.ncomp(), N, JK_dev);
+  finalize_k_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, h->stream>>>(h->d_Kh, JK_dev + nn, N);
   CUDA_OK(cudaGetLastError());
-  h->stats.launches += 1;
+  h->stats.launches += 2 * (int)h->batches.size() + 1;
   return RCHEM_OK;
 }
 

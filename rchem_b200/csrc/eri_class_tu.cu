@@ -1,10 +1,9 @@
 // eri_class_tu.cu -- one translation unit per angular-momentum class.
-// Compiled 21 times with -DRCHEM_LA=.. -DRCHEM_LB=.. -DRCHEM_LC=.. -DRCHEM_LD=.. and
-// -DRCHEM_TAG=<abcd> (see rchem_b200/csrc/Makefile), so the classes build in parallel.
+// Compiled 21 times with -DRCHEM_LA=.. -DRCHEM_LB=.. -DRCHEM_LC=.. -DRCHEM_LD=..,
+// -DRCHEM_TAG=<abcd> and -DRCHEM_INC="gen/eri_class_<abcd>.inc" (see Makefile), so the
+// classes build in parallel.
 #include "eri_kernel.cuh"
 
-#define RCHEM_STR2(x) #x
-#define RCHEM_STR(x) RCHEM_STR2(x)
 #define RCHEM_CAT2(a, b) a##b
 #define RCHEM_CAT(a, b) RCHEM_CAT2(a, b)
 
@@ -34,6 +33,33 @@ cudaError_t RCHEM_CAT(launch_eri_, RCHEM_TAG)(int boys, int mode, const EriTask&
                                   : launch_one<kBoysExact, kModeSchwarz>(task, grid, stream);
 #endif
   return cudaErrorInvalidValue;
+}
+
+// block-per-bra-pair J/K kernel
+template <int BOYS>
+static cudaError_t launch_block(const EriTask& task, unsigned grid, size_t smem,
+                                cudaStream_t stream) {
+  auto kern = eri_jk_block_kernel<RCHEM_LA, RCHEM_LB, RCHEM_LC, RCHEM_LD, BOYS>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  kern<<<grid, BlockCfg<RCHEM_LA, RCHEM_LB, RCHEM_LC, RCHEM_LD>::kThreadsBlk, smem, stream>>>(task);
+  return cudaGetLastError();
+}
+
+cudaError_t RCHEM_CAT(launch_eri_block_, RCHEM_TAG)(int boys, const EriTask& task, unsigned grid,
+                                                    size_t smem, cudaStream_t stream) {
+  if (grid == 0) return cudaSuccess;
+  return boys == kBoysReference ? launch_block<kBoysReference>(task, grid, smem, stream)
+                                : launch_block<kBoysExact>(task, grid, smem, stream);
+}
+
+EriBlockInfo RCHEM_CAT(block_info_, RCHEM_TAG)() {
+  using Cfg = BlockCfg<RCHEM_LA, RCHEM_LB, RCHEM_LC, RCHEM_LD>;
+  return EriBlockInfo{Cfg::kThreadsBlk, Cfg::kKetsPerBlock};
 }
 
 }  // namespace rchem

@@ -36,6 +36,8 @@ struct BatchView {
   const double* prim;
   const double* geom;
   const int* idx;
+  const double* Dp;  // [ncart(la)*ncart(lb)][stride]  D block of every pair, pair-major packed
+  double* Jp;        // [ncart(la)*ncart(lb)][stride]  J block of every pair (accumulated)
   int npairs;
   int stride;
   int K2;
@@ -50,8 +52,12 @@ struct EriTask {
   int rank, nranks;              // multi-GPU: this process takes blocks b with b % nranks == rank
   int N;                         // number of basis functions
   const double* D;               // [N][N] density (symmetric)            kModeJK
-  double* Jh;                    // [N][N] half-accumulated J             kModeJK
   double* Kh;                    // [N][N] half-accumulated K             kModeJK
+  // block-per-bra-pair J/K kernel (eri_jk_block_kernel): "heavy" bra pairs only
+  const int* hp;                 // [nheavy]   bra pair index of heavy entry h
+  const long long* hblk_prefix;  // [nheavy+1] running block count
+  long long nblocks_heavy;
+  int nheavy;
   double* I;                     // [N]^4 dense tensor                    kModeTensor
   double* Qout;                  // [bra.npairs] Schwarz bounds           kModeSchwarz
   const double* boys_table;      // exact-Boys grid (eri_core.h)
@@ -77,6 +83,83 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---------------------------------------------------------------------------------------
+// One contracted shell quartet (bra pair p | ket pair q) of a task: primitive loop, HRR,
+// component norms.  Returns the degeneracy factor of the quartet under the 8 permutations.
+// ---------------------------------------------------------------------------------------
+struct BraGeom {
+  double Ax, Ay, Az, ABx, ABy, ABz;
+  int diag;
+};
+
+__device__ __forceinline__ BraGeom load_bra_geom(const BatchView& bra, int p) {
+  const double* gb = bra.geom + p;
+  const int sb = bra.stride;
+  BraGeom g;
+  g.Ax = __ldg(gb); g.Ay = __ldg(gb + sb); g.Az = __ldg(gb + 2 * sb);
+  g.ABx = __ldg(gb + 3 * sb); g.ABy = __ldg(gb + 4 * sb); g.ABz = __ldg(gb + 5 * sb);
+  g.diag = __ldg(bra.idx + 2 * sb + p);
+  return g;
+}
+
+// BRA_SMEM: the bra pair's primitive pairs were staged in shared memory (block kernel);
+// otherwise they are read (warp-uniformly) from the SoA arrays.
+template <class C, int LA, int LB, int LC, int LD, int BOYS, bool BRA_SMEM>
+__device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const BraGeom& g,
+                                                const PrimPair* __restrict__ s_bra, int q,
+                                                double* __restrict__ out, int& bfC, int& bfD) {
+  constexpr int NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
+  constexpr bool kUnroll = C::kOut <= 81;
+  const double* gk = t.ket.geom + q;
+  const int sk = t.ket.stride;
+  const double Cx = __ldg(gk), Cy = __ldg(gk + sk), Cz = __ldg(gk + 2 * sk);
+
+  double acc[C::kTargets];
+#pragma unroll
+  for (int i = 0; i < C::kTargets; ++i) acc[i] = 0.0;
+
+  const int K2b = t.bra.K2, K2k = t.ket.K2;
+  for (int kk = 0; kk < K2k; ++kk) {
+    const PrimPair pk = load_prim(t.ket, kk, q);
+    for (int kb = 0; kb < K2b; ++kb) {
+      if (BRA_SMEM) {
+        primitive_quartet<C, BOYS>(s_bra[kb], pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys_table, acc);
+      } else {
+        const PrimPair pb = load_prim(t.bra, kb, p);
+        primitive_quartet<C, BOYS>(pb, pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys_table, acc);
+      }
+    }
+  }
+  C::hrr(acc, g.ABx, g.ABy, g.ABz, __ldg(gk + 3 * sk), __ldg(gk + 4 * sk), __ldg(gk + 5 * sk), out);
+
+  if (LA >= 2 || LB >= 2 || LC >= 2 || LD >= 2) {  // per-component norm ratios (d and up)
+#pragma unroll(kUnroll ? C::kOut : 1)
+    for (int i = 0; i < C::kOut; ++i) {
+      const int d = i % ND, c = (i / ND) % NC, b = (i / (ND * NC)) % NB, a = i / (ND * NC * NB);
+      out[i] *= t.compscale[LA][a] * t.compscale[LB][b] * t.compscale[LC][c] * t.compscale[LD][d];
+    }
+  }
+  bfC = __ldg(t.ket.idx + q);
+  bfD = __ldg(t.ket.idx + sk + q);
+  // degeneracy of the shell quartet under the 8 index permutations
+  double scale = 1.0;
+  if (g.diag) scale *= 0.5;
+  if (__ldg(t.ket.idx + 2 * sk + q)) scale *= 0.5;
+  if (t.same && p == q) scale *= 0.5;
+  return scale;
+}
+
+// ---------------------------------------------------------------------------------------
+// Warp-task kernel: one warp per (bra pair, 32 consecutive kets).  Used for the dense tensor,
+// the Schwarz bounds, and the J/K digestion of "light" bra pairs (few surviving kets).
+//
+// J/K digestion (derived from basis.rs:406-417 for symmetric D): with
+// v = s*(ab|cd), s the degeneracy factor,
+//   J[ab] += 2 v D[cd]     J[cd] += 2 v D[ab]
+//   Kh[ac] += v D[bd]  Kh[ad] += v D[bc]  Kh[bc] += v D[ad]  Kh[bd] += v D[ac],  K = Kh + Kh^T.
+// J and the D blocks it needs live PAIR-PACKED (BatchView::Jp / Dp), so lanes touch
+// consecutive addresses; finalize_j_kernel scatters Jp into the N x N matrix.
+// ---------------------------------------------------------------------------------------
 template <int LA, int LB, int LC, int LD, int BOYS, int MODE>
 __global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
   using C = EriClass<LA, LB, LC, LD>;
@@ -105,48 +188,11 @@ __global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
   }
 
   double out[C::kOut];
-  int bfA = 0, bfB = 0, bfC = 0, bfD = 0;
+  int bfC = 0, bfD = 0;
   double scale = 0.0;
-
   if (active) {
-    const double* gb = t.bra.geom + p;
-    const double* gk = t.ket.geom + q;
-    const int sb = t.bra.stride, sk = t.ket.stride;
-    const double Ax = __ldg(gb), Ay = __ldg(gb + sb), Az = __ldg(gb + 2 * sb);
-    const double Cx = __ldg(gk), Cy = __ldg(gk + sk), Cz = __ldg(gk + 2 * sk);
-
-    double acc[C::kTargets];
-#pragma unroll
-    for (int i = 0; i < C::kTargets; ++i) acc[i] = 0.0;
-
-    const int K2b = t.bra.K2, K2k = t.ket.K2;
-    for (int kk = 0; kk < K2k; ++kk) {
-      const PrimPair pk = load_prim(t.ket, kk, q);
-      for (int kb = 0; kb < K2b; ++kb) {
-        const PrimPair pb = load_prim(t.bra, kb, p);
-        primitive_quartet<C, BOYS>(pb, pk, Ax, Ay, Az, Cx, Cy, Cz, t.boys_table, acc);
-      }
-    }
-    C::hrr(acc, __ldg(gb + 3 * sb), __ldg(gb + 4 * sb), __ldg(gb + 5 * sb), __ldg(gk + 3 * sk),
-           __ldg(gk + 4 * sk), __ldg(gk + 5 * sk), out);
-
-    if (LA >= 2 || LB >= 2 || LC >= 2 || LD >= 2) {  // per-component norm ratios (d and up)
-#pragma unroll(kUnroll ? C::kOut : 1)
-      for (int i = 0; i < C::kOut; ++i) {
-        const int d = i % ND, c = (i / ND) % NC, b = (i / (ND * NC)) % NB, a = i / (ND * NC * NB);
-        out[i] *= t.compscale[LA][a] * t.compscale[LB][b] * t.compscale[LC][c] * t.compscale[LD][d];
-      }
-    }
-
-    bfA = __ldg(t.bra.idx + p);
-    bfB = __ldg(t.bra.idx + sb + p);
-    bfC = __ldg(t.ket.idx + q);
-    bfD = __ldg(t.ket.idx + sk + q);
-    // degeneracy of the shell quartet under the 8 index permutations
-    scale = 1.0;
-    if (__ldg(t.bra.idx + 2 * sb + p)) scale *= 0.5;
-    if (__ldg(t.ket.idx + 2 * sk + q)) scale *= 0.5;
-    if (t.same && p == q) scale *= 0.5;
+    const BraGeom g = load_bra_geom(t.bra, min(p, t.bra.npairs - 1));
+    scale = shell_quartet<C, LA, LB, LC, LD, BOYS, false>(t, p, g, nullptr, q, out, bfC, bfD);
   }
 
   if (MODE == kModeSchwarz) {
@@ -159,9 +205,11 @@ __global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
     return;
   }
 
+  const int sb = t.bra.stride, sk = t.ket.stride;
   if (MODE == kModeTensor) {
     if (active) {
       const size_t N = (size_t)t.N;
+      const int bfA = __ldg(t.bra.idx + p), bfB = __ldg(t.bra.idx + sb + p);
       double* __restrict__ I = t.I;
 #pragma unroll(kUnroll ? C::kOut : 1)
       for (int o = 0; o < C::kOut; ++o) {
@@ -181,12 +229,7 @@ __global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
     return;
   }
 
-  // ---- kModeJK: digest the block against D -------------------------------------------
-  //   Jh[ab] += 2 s v D[cd]     Jh[cd] += 2 s v D[ab]
-  //   Kh[ac] += s v D[bd]  Kh[ad] += s v D[bc]  Kh[bc] += s v D[ad]  Kh[bd] += s v D[ac]
-  // and J = Jh + Jh^T, K = Kh + Kh^T afterwards (finalize kernel).  s is the degeneracy
-  // factor; D is symmetric.  See DESIGN.md "J/K digestion" for the derivation from
-  // basis.rs:406-417.
+  // ---- kModeJK ---------------------------------------------------------------------------
   {
     const int N = t.N;
     const double* __restrict__ D = t.D;
@@ -204,16 +247,13 @@ __global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
 #pragma unroll
     for (int i = 0; i < NB * ND; ++i) kbd[i] = 0.0;
 
+    const int bfA = __ldg(t.bra.idx + p), bfB = __ldg(t.bra.idx + sb + p);  // warp-uniform
     if (active) {
       double Dab[NA * NB], Dcd[NC * ND], Dac[NA * NC], Dad[NA * ND], Dbc[NB * NC], Dbd[NB * ND];
 #pragma unroll
-      for (int a = 0; a < NA; ++a)
+      for (int i = 0; i < NA * NB; ++i) Dab[i] = __ldg(t.bra.Dp + (size_t)i * sb + p);
 #pragma unroll
-        for (int b = 0; b < NB; ++b) Dab[a * NB + b] = __ldg(D + (size_t)(bfA + a) * N + bfB + b);
-#pragma unroll
-      for (int c = 0; c < NC; ++c)
-#pragma unroll
-        for (int d = 0; d < ND; ++d) Dcd[c * ND + d] = __ldg(D + (size_t)(bfC + c) * N + bfD + d);
+      for (int i = 0; i < NC * ND; ++i) Dcd[i] = __ldg(t.ket.Dp + (size_t)i * sk + q);
 #pragma unroll
       for (int a = 0; a < NA; ++a)
 #pragma unroll
@@ -245,17 +285,15 @@ __global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
       }
     }
 
-    // bra-pair row of J: every lane of the warp shares (a,b) -> reduce, one atomic per warp
-    const int bfA0 = __shfl_sync(0xffffffffu, bfA, 0), bfB0 = __shfl_sync(0xffffffffu, bfB, 0);
+    // bra-pair block of J: every lane of the warp shares (a,b) -> reduce, one atomic per warp
 #pragma unroll
     for (int i = 0; i < NA * NB; ++i) {
       const double s = warp_sum(jab[i]);
-      if (lane == 0) atomicAdd(t.Jh + (size_t)(bfA0 + i / NB) * N + bfB0 + i % NB, s);
+      if (lane == 0) atomicAdd(t.bra.Jp + (size_t)i * sb + p, s);
     }
     if (active) {
 #pragma unroll
-      for (int i = 0; i < NC * ND; ++i)
-        atomicAdd(t.Jh + (size_t)(bfC + i / ND) * N + bfD + i % ND, jcd[i]);
+      for (int i = 0; i < NC * ND; ++i) atomicAdd(t.ket.Jp + (size_t)i * sk + q, jcd[i]);
 #pragma unroll
       for (int i = 0; i < NA * NC; ++i)
         atomicAdd(t.Kh + (size_t)(bfA + i / NC) * N + bfC + i % NC, kac[i]);
@@ -272,8 +310,160 @@ __global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
   }
 }
 
-// Host-side launcher signature, one per class (eri_class_launch.cu.in)
+// ---------------------------------------------------------------------------------------
+// Block-per-bra-pair J/K kernel for "heavy" bra pairs (many surviving kets).  A block owns
+// one bra pair (A,B) and a contiguous range of its ket prefix.  The rows D[a,:], D[b,:] and
+// the accumulators K[a,:], K[b,:] (a in A, b in B) live in SHARED memory, so the four
+// mixed-index K updates and their density factors never touch L1/L2 with scattered 8-byte
+// accesses; the bra block of J accumulates in registers over the whole ket range.
+// Dynamic shared memory: 2*(NA+NB)*N doubles + K2_bra primitive pairs.
+// ---------------------------------------------------------------------------------------
+#ifndef RCHEM_BLK_T_SMALL
+#define RCHEM_BLK_T_SMALL 384
+#endif
+#ifndef RCHEM_BLK_MINB_SMALL
+#define RCHEM_BLK_MINB_SMALL 2
+#endif
+template <int LA, int LB, int LC, int LD> struct BlockCfg {
+  // small classes: RCHEM_BLK_T_SMALL threads; large ones (register-heavy): 256 threads
+  static constexpr bool kSmall = EriClass<LA, LB, LC, LD>::kTargets <= 9;
+  static constexpr int kThreadsBlk = kSmall ? RCHEM_BLK_T_SMALL : 256;
+  static constexpr int kMinBlocks = kSmall ? RCHEM_BLK_MINB_SMALL : 1;
+  static constexpr int kKetsPerBlock = kThreadsBlk * 8;
+};
+
+__device__ __forceinline__ void smem_add(double* addr, double v) { atomicAdd(addr, v); }
+
+template <int LA, int LB, int LC, int LD, int BOYS>
+__global__ void __launch_bounds__(BlockCfg<LA, LB, LC, LD>::kThreadsBlk,
+                                  BlockCfg<LA, LB, LC, LD>::kMinBlocks)
+eri_jk_block_kernel(const EriTask t) {
+  using C = EriClass<LA, LB, LC, LD>;
+  constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
+  constexpr bool kUnroll = C::kOut <= 81;
+  constexpr int T = BlockCfg<LA, LB, LC, LD>::kThreadsBlk;
+  extern __shared__ double smem[];
+  __shared__ int s_info[3];
+
+  const long long blk = (long long)blockIdx.x * t.nranks + t.rank;
+  if (blk >= t.nblocks_heavy) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) {
+    int lo = 0, hi = t.nheavy;  // hblk_prefix[lo] <= blk < hblk_prefix[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(t.hblk_prefix + mid) <= blk) lo = mid; else hi = mid;
+    }
+    const int p = __ldg(t.hp + lo);
+    const int nq = __ldg(t.nq + p);
+    const long long first = __ldg(t.hblk_prefix + lo);
+    const int nb = (int)(__ldg(t.hblk_prefix + lo + 1) - first);
+    const int per = (((nq + nb - 1) / nb) + 31) & ~31;
+    const int q0 = (int)(blk - first) * per;
+    s_info[0] = p;
+    s_info[1] = q0;
+    s_info[2] = min(nq, q0 + per);
+  }
+  __syncthreads();
+  const int p = s_info[0], q0 = s_info[1], q1 = s_info[2];
+  const int N = t.N, sb = t.bra.stride, sk = t.ket.stride;
+  const int bfA = __ldg(t.bra.idx + p), bfB = __ldg(t.bra.idx + sb + p);
+
+  double* Drow_a = smem;                 // [NA][N]
+  double* Drow_b = Drow_a + NA * N;      // [NB][N]
+  double* Krow_a = Drow_b + NB * N;      // [NA][N]
+  double* Krow_b = Krow_a + NA * N;      // [NB][N]
+  PrimPair* s_bra = reinterpret_cast<PrimPair*>(Krow_b + NB * N);  // [K2_bra]
+  for (int k = tid; k < t.bra.K2; k += T) s_bra[k] = load_prim(t.bra, k, p);
+  const BraGeom g = load_bra_geom(t.bra, p);
+  for (int a = 0; a < NA; ++a)
+    for (int j = tid; j < N; j += T) {
+      Drow_a[a * N + j] = __ldg(t.D + (size_t)(bfA + a) * N + j);
+      Krow_a[a * N + j] = 0.0;
+    }
+  for (int b = 0; b < NB; ++b)
+    for (int j = tid; j < N; j += T) {
+      Drow_b[b * N + j] = __ldg(t.D + (size_t)(bfB + b) * N + j);
+      Krow_b[b * N + j] = 0.0;
+    }
+  double Dab[NA * NB], jab[NA * NB];
+#pragma unroll
+  for (int i = 0; i < NA * NB; ++i) {
+    Dab[i] = __ldg(t.bra.Dp + (size_t)i * sb + p);
+    jab[i] = 0.0;
+  }
+  __syncthreads();
+
+  for (int q = q0 + tid; q < q1; q += T) {
+    double out[C::kOut];
+    int bfC, bfD;
+    const double scale =
+        shell_quartet<C, LA, LB, LC, LD, BOYS, true>(t, p, g, s_bra, q, out, bfC, bfD);
+
+    double jcd[NC * ND], kac[NA * NC], kad[NA * ND], kbc[NB * NC], kbd[NB * ND], Dcd[NC * ND];
+#pragma unroll
+    for (int i = 0; i < NC * ND; ++i) { jcd[i] = 0.0; Dcd[i] = __ldg(t.ket.Dp + (size_t)i * sk + q); }
+#pragma unroll
+    for (int i = 0; i < NA * NC; ++i) kac[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NA * ND; ++i) kad[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NB * NC; ++i) kbc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NB * ND; ++i) kbd[i] = 0.0;
+    const double* Da_c = Drow_a + bfC;
+    const double* Da_d = Drow_a + bfD;
+    const double* Db_c = Drow_b + bfC;
+    const double* Db_d = Drow_b + bfD;
+#pragma unroll(kUnroll ? C::kOut : 1)
+    for (int o = 0; o < C::kOut; ++o) {
+      const int d = o % ND, c = (o / ND) % NC, b = (o / (ND * NC)) % NB, a = o / (ND * NC * NB);
+      const double v = scale * out[o];
+      const double v2 = v + v;
+      jab[a * NB + b] = fma(v2, Dcd[c * ND + d], jab[a * NB + b]);
+      jcd[c * ND + d] = fma(v2, Dab[a * NB + b], jcd[c * ND + d]);
+      kac[a * NC + c] = fma(v, Db_d[b * N + d], kac[a * NC + c]);
+      kad[a * ND + d] = fma(v, Db_c[b * N + c], kad[a * ND + d]);
+      kbc[b * NC + c] = fma(v, Da_d[a * N + d], kbc[b * NC + c]);
+      kbd[b * ND + d] = fma(v, Da_c[a * N + c], kbd[b * ND + d]);
+    }
+#pragma unroll
+    for (int i = 0; i < NC * ND; ++i) atomicAdd(t.ket.Jp + (size_t)i * sk + q, jcd[i]);
+#pragma unroll
+    for (int i = 0; i < NA * NC; ++i) smem_add(Krow_a + (i / NC) * N + bfC + i % NC, kac[i]);
+#pragma unroll
+    for (int i = 0; i < NA * ND; ++i) smem_add(Krow_a + (i / ND) * N + bfD + i % ND, kad[i]);
+#pragma unroll
+    for (int i = 0; i < NB * NC; ++i) smem_add(Krow_b + (i / NC) * N + bfC + i % NC, kbc[i]);
+#pragma unroll
+    for (int i = 0; i < NB * ND; ++i) smem_add(Krow_b + (i / ND) * N + bfD + i % ND, kbd[i]);
+  }
+
+  // bra block of J: registers -> warp reduce -> one atomic per warp and component
+#pragma unroll
+  for (int i = 0; i < NA * NB; ++i) {
+    const double s = warp_sum(jab[i]);
+    if (lane == 0 && s != 0.0) atomicAdd(t.bra.Jp + (size_t)i * sb + p, s);
+  }
+  __syncthreads();
+  // flush the K rows (only touched entries)
+  for (int a = 0; a < NA; ++a)
+    for (int j = tid; j < N; j += T) {
+      const double v = Krow_a[a * N + j];
+      if (v != 0.0) atomicAdd(t.Kh + (size_t)(bfA + a) * N + j, v);
+    }
+  for (int b = 0; b < NB; ++b)
+    for (int j = tid; j < N; j += T) {
+      const double v = Krow_b[b * N + j];
+      if (v != 0.0) atomicAdd(t.Kh + (size_t)(bfB + b) * N + j, v);
+    }
+}
+
+// Host-side launcher signatures, one pair per class (eri_class_tu.cu)
 typedef cudaError_t (*EriLaunchFn)(int boys, int mode, const EriTask& task, unsigned grid,
                                    cudaStream_t stream);
+typedef cudaError_t (*EriBlockLaunchFn)(int boys, const EriTask& task, unsigned grid,
+                                        size_t smem_bytes, cudaStream_t stream);
+struct EriBlockInfo { int threads; int kets_per_block; };
 
 }  // namespace rchem

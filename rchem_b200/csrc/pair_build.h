@@ -34,14 +34,16 @@ inline void build_prim_pairs(const Shell& A, const Shell& B, std::vector<PrimPai
     }
 }
 
-// exact Boys table for boys_exact (eri_core.h): rows x = i/kBoysPerUnit, columns m
-inline void build_boys_table(std::vector<double>* table) {
-  table->assign((size_t)kBoysRows * kBoysCols, 0.0);
+// exact Boys tables for boys_exact (eri_core.h): one table per total angular momentum
+// L = 0..kBoysMaxL, rows x_i = i/kBoysPerUnit, row = {F_{L+k}(x_i)/k! (k=0..7), exp(-x_i), 0}.
+inline void build_boys_tables(std::vector<double>* tables) {
+  const int mtop = kBoysMaxL + 7;
+  tables->assign((size_t)(kBoysMaxL + 1) * kBoysTableLen, 0.0);
+  std::vector<long double> F(mtop + 1);
   for (int i = 0; i < kBoysRows; ++i) {
     const long double x = (long double)i / kBoysPerUnit;
     // top order by the all-positive series e^-x sum_k (2x)^k / ((2m+1)(2m+3)..(2m+2k+1)),
     // lower orders by the stable downward recursion
-    const int mtop = kBoysCols - 1;
     long double term = 1.0L / (2 * mtop + 1), sum = term;
     for (int k = 1; k < 2000; ++k) {
       term *= 2.0L * x / (2 * mtop + 2 * k + 1);
@@ -49,11 +51,17 @@ inline void build_boys_table(std::vector<double>* table) {
       if (term < 1e-24L * sum) break;
     }
     const long double ex = expl(-x);
-    long double f = ex * sum;
-    (*table)[(size_t)i * kBoysCols + mtop] = (double)f;
-    for (int m = mtop; m > 0; --m) {
-      f = (2.0L * x * f + ex) / (2 * m - 1);
-      (*table)[(size_t)i * kBoysCols + m - 1] = (double)f;
+    F[mtop] = ex * sum;
+    for (int m = mtop; m > 0; --m) F[m - 1] = (2.0L * x * F[m] + ex) / (2 * m - 1);
+    for (int L = 0; L <= kBoysMaxL; ++L) {
+      double* row = tables->data() + (size_t)L * kBoysTableLen + (size_t)i * kBoysRowLen;
+      long double fact = 1.0L;
+      for (int k = 0; k < 8; ++k) {
+        if (k > 0) fact *= k;
+        row[k] = (double)(F[L + k] / fact);
+      }
+      row[8] = (double)ex;
+      row[9] = 0.0;
     }
   }
 }

@@ -244,11 +244,13 @@ def classes(lmax=LMAX):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--outdir", default=os.path.join(os.path.dirname(__file__), "..", "csrc", "gen"))
+    ap.add_argument("--lmax", type=int, default=LMAX,
+                    help="highest shell angular momentum (2 = s,p,d: 21 classes; 1 is a fast dev build)")
     args = ap.parse_args()
     os.makedirs(args.outdir, exist_ok=True)
     table = {}
     tags = []
-    for (la, lb, lc, ld) in classes():
+    for (la, lb, lc, ld) in classes(args.lmax):
         tag, src, info = gen_class(la, lb, lc, ld)
         with open(os.path.join(args.outdir, f"eri_class_{tag}.inc"), "w") as fh:
             fh.write(src)

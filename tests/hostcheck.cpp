@@ -107,14 +107,15 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
   std::string err;
   if (!group_shells(b, &ss, &err)) return -1;
   static std::vector<double> table;
-  if (table.empty()) build_boys_table(&table);
+  if (table.empty()) build_boys_tables(&table);
   const Shell &A = ss.shells[sa], &B = ss.shells[sb], &C = ss.shells[sc], &D = ss.shells[sd];
 #define X(la, lb, lc, ld, tag)                                                              \
   if (A.l == la && B.l == lb && C.l == lc && D.l == ld) {                                   \
     if (boys == kBoysReference)                                                             \
       shell_quartet<EriClass<la, lb, lc, ld>, kBoysReference>(ss, A, B, C, D, table.data(), out); \
     else                                                                                    \
-      shell_quartet<EriClass<la, lb, lc, ld>, kBoysExact>(ss, A, B, C, D, table.data(), out);     \
+      shell_quartet<EriClass<la, lb, lc, ld>, kBoysExact>(                                  \
+          ss, A, B, C, D, table.data() + (la + lb + lc + ld) * kBoysTableLen, out);         \
     return EriClass<la, lb, lc, ld>::kOut;                                                  \
   }
   RCHEM_ERI_CLASSES(X)
@@ -124,7 +125,7 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
 
 extern "C" void hostcheck_boys(int boys, int L, double x, double* F) {
   static std::vector<double> table;
-  if (table.empty()) build_boys_table(&table);
+  if (table.empty()) build_boys_tables(&table);
   // L <= 8
   if (boys == kBoysReference) {
     switch (L) {
@@ -136,9 +137,9 @@ extern "C" void hostcheck_boys(int boys, int L, double x, double* F) {
   } else {
     switch (L) {
       case 0: boys_exact<0>(x, table.data(), F); break;
-      case 2: boys_exact<2>(x, table.data(), F); break;
-      case 4: boys_exact<4>(x, table.data(), F); break;
-      default: boys_exact<8>(x, table.data(), F); break;
+      case 2: boys_exact<2>(x, table.data() + 2 * kBoysTableLen, F); break;
+      case 4: boys_exact<4>(x, table.data() + 4 * kBoysTableLen, F); break;
+      default: boys_exact<8>(x, table.data() + 8 * kBoysTableLen, F); break;
     }
   }
 }
