@@ -331,6 +331,22 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    # ---- the other Boys flavour, same workload, device-resident (reported alongside) ----------
+    other = rc.BOYS_EXACT if args.boys == "reference" else rc.BOYS_REFERENCE
+    basis.set_boys(other)
+    step_resident()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    other_ms = float(t.item()) / args.steps
+    other_kernel_ms = basis.stats()["kernel_ms"]
+    basis.set_boys(rc.BOYS_REFERENCE if args.boys == "reference" else rc.BOYS_EXACT)
     clocks = sampler.stop()
 
     # ---- whole-job counts ---------------------------------------------------------------------
@@ -347,6 +363,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
+    peak_best, peak_avg = rc.fp64_peak(local, 10)
     ms_per_step = ms_total / args.steps
     value = sq / (ms_per_step * 1e-3)
     e2e_value = sq / (e2e_s / args.steps)
@@ -374,13 +391,20 @@ def run_ours(args):
         "clocks": clocks,
     }
     # ---- roofline: FP64 pipe --------------------------------------------------------------------
-    peak_best, peak_avg = rc.fp64_peak(local, 10)
     if world == 1:
         k_ms = float(np.mean(kernel_ms))
         achieved = flops / (k_ms * 1e-3) / 1e12
     else:
         k_ms = ms_per_step
         achieved = flops / (k_ms * 1e-3) / 1e12 / world
+    other_name = "exact_boys" if args.boys == "reference" else "reference_boys"
+    line[other_name] = {
+        "note": "same workload with the other Boys flavour (SURVEY H1: exact = converged tabulated "
+                "Boys, <=2e-8 from libpyquante2; reference = libpyquante2 Fgamma, 1e-12 parity)",
+        "value": sq / (other_ms * 1e-3), "unit": UNIT, "ms_per_step": other_ms,
+        "roofline_frac": (flops / ((other_kernel_ms if world == 1 else other_ms) * 1e-3) / 1e12
+                          / (world if world > 1 else 1)) / peak_avg,
+    }
     line["roofline"] = {
         "bound": "fp64", "achieved": achieved, "peak": peak_avg, "unit": "TFLOP/s",
         "frac": achieved / peak_avg, "traffic": None,

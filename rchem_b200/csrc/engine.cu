@@ -207,7 +207,8 @@ struct rchem_basis {
   std::vector<Batch> batches;
   std::vector<TaskTable> tasks;
   double tasks_tau = -1.0;
-  double* d_boys = nullptr;
+  double* d_boys = nullptr;      // exact-Boys grids, one per L
+  double* d_boys_ref = nullptr;  // reference-Boys step tables
   double *d_D = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   rchem_stats stats{};
@@ -304,6 +305,11 @@ int ensure_ready(rchem_basis* h) {
   build_boys_tables(&table);
   CUDA_OK(cudaMalloc(&h->d_boys, table.size() * sizeof(double)));
   CUDA_OK(cudaMemcpy(h->d_boys, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
+  std::vector<double> rtable;
+  if (!build_boys_ref_tables(&rtable))
+    return fail(RCHEM_ERR_CUDA, "internal: reference-Boys step table has a cell with two steps");
+  CUDA_OK(cudaMalloc(&h->d_boys_ref, rtable.size() * sizeof(double)));
+  CUDA_OK(cudaMemcpy(h->d_boys_ref, rtable.data(), rtable.size() * sizeof(double), cudaMemcpyHostToDevice));
 
   // shell pairs -> batches keyed by (la, lb, K2); batch order = pair class, then K2 descending
   const auto& sh = h->shells.shells;
@@ -466,6 +472,7 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
     t.bra = B.view();
     t.ket = K.view();
     t.boys_table = h->d_boys + (size_t)(B.la + B.lb + K.la + K.lb) * kBoysTableLen;
+    t.boys_ref_table = h->d_boys_ref;
     t.nq = tt.d_nq;
     t.same = tt.bra == tt.ket;
     t.rank = rank;
@@ -599,7 +606,7 @@ void rchem_basis_destroy(rchem_basis* h) {
     for (Batch& bt : h->batches) {
       cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_idx); cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
     }
-    cudaFree(h->d_boys); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK);
+    cudaFree(h->d_boys); cudaFree(h->d_boys_ref); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
   }

@@ -70,6 +70,7 @@ def hostcheck():
     H.hostcheck_shell_quartet.argtypes = [C.c_int, dp, ip, ip, dp, dp, dp] + [C.c_int] * 5 + [dp]
     H.hostcheck_boys.argtypes = [C.c_int, C.c_int, C.c_double, dp]
     H.hostcheck_boys.restype = None
+    H.hostcheck_ref_tables_ok.restype = C.c_int
     return H
 
 

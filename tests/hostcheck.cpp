@@ -38,7 +38,7 @@ namespace rchem {
 
 template <class C, int BOYS>
 void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const Shell& Cc,
-                   const Shell& D, const double* table, double* out) {
+                   const Shell& D, const double* table, const double* rtable, double* out) {
   std::vector<PrimPair> bra, ket;
   build_prim_pairs(A, B, &bra);
   build_prim_pairs(Cc, D, &ket);
@@ -46,7 +46,7 @@ void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const She
   for (const PrimPair& k : ket)
     for (const PrimPair& b : bra)
       primitive_quartet<C, BOYS>(b, k, A.ctr[0], A.ctr[1], A.ctr[2], Cc.ctr[0], Cc.ctr[1],
-                                 Cc.ctr[2], table, acc.data());
+                                 Cc.ctr[2], table, rtable, acc.data());
   C::hrr(acc.data(), A.ctr[0] - B.ctr[0], A.ctr[1] - B.ctr[1], A.ctr[2] - B.ctr[2],
          Cc.ctr[0] - D.ctr[0], Cc.ctr[1] - D.ctr[1], Cc.ctr[2] - D.ctr[2], out);
   const int na = ncart(A.l), nb = ncart(B.l), nc = ncart(Cc.l), nd = ncart(D.l);
@@ -106,16 +106,17 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
   ShellSet ss;
   std::string err;
   if (!group_shells(b, &ss, &err)) return -1;
-  static std::vector<double> table;
-  if (table.empty()) build_boys_tables(&table);
+  static std::vector<double> table, rtable;
+  if (table.empty()) { build_boys_tables(&table); build_boys_ref_tables(&rtable); }
   const Shell &A = ss.shells[sa], &B = ss.shells[sb], &C = ss.shells[sc], &D = ss.shells[sd];
 #define X(la, lb, lc, ld, tag)                                                              \
   if (A.l == la && B.l == lb && C.l == lc && D.l == ld) {                                   \
     if (boys == kBoysReference)                                                             \
-      shell_quartet<EriClass<la, lb, lc, ld>, kBoysReference>(ss, A, B, C, D, table.data(), out); \
+      shell_quartet<EriClass<la, lb, lc, ld>, kBoysReference>(                              \
+          ss, A, B, C, D, table.data() + (la + lb + lc + ld) * kBoysTableLen, rtable.data(), out); \
     else                                                                                    \
       shell_quartet<EriClass<la, lb, lc, ld>, kBoysExact>(                                  \
-          ss, A, B, C, D, table.data() + (la + lb + lc + ld) * kBoysTableLen, out);         \
+          ss, A, B, C, D, table.data() + (la + lb + lc + ld) * kBoysTableLen, rtable.data(), out); \
     return EriClass<la, lb, lc, ld>::kOut;                                                  \
   }
   RCHEM_ERI_CLASSES(X)
@@ -123,16 +124,23 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
   return -2;
 }
 
+extern "C" int hostcheck_ref_tables_ok() {
+  std::vector<double> t;
+  return build_boys_ref_tables(&t) ? 1 : 0;
+}
+
+// boys: 0 = fast reference path, 1 = exact, 2 = faithful reference loops
 extern "C" void hostcheck_boys(int boys, int L, double x, double* F) {
-  static std::vector<double> table;
-  if (table.empty()) build_boys_tables(&table);
+  static std::vector<double> table, rtable;
+  if (table.empty()) { build_boys_tables(&table); build_boys_ref_tables(&rtable); }
+  if (boys == 2) { boys_reference_faithful<8>(x, F); return; }
   // L <= 8
   if (boys == kBoysReference) {
     switch (L) {
-      case 0: boys_reference<0>(x, F); break;
-      case 2: boys_reference<2>(x, F); break;
-      case 4: boys_reference<4>(x, F); break;
-      default: boys_reference<8>(x, F); break;
+      case 0: boys_reference<0>(x, rtable.data(), F); break;
+      case 2: boys_reference<2>(x, rtable.data(), F); break;
+      case 4: boys_reference<4>(x, rtable.data(), F); break;
+      default: boys_reference<8>(x, rtable.data(), F); break;
     }
   } else {
     switch (L) {

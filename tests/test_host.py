@@ -161,14 +161,35 @@ def test_all_21_classes_against_oracle(hostcheck, orc, geo, ref_or_restated):
 def test_boys_reference_restatement_bitwise_iterations(hostcheck, orc):
     g = golden("fgamma_ref.npz")
     F = np.zeros(9)
+    for mode in (2, 0):  # 2 = faithful loops, 0 = fast table-driven path
+        worst = 0.0
+        for j, x in enumerate(g["x"]):
+            hostcheck.hostcheck_boys(mode, 8, float(x), F)
+            ref = g["F"][:9, j]
+            worst = max(worst, np.abs(F / ref - 1).max())
+        # same loops, same iteration counts; only the smooth wrapper differs: the reference forms
+        # exp(-x + a ln x - lgamma a) whose argument carries ~|arg| ulp of rounding noise
+        assert worst < 1e-13, (mode, worst)
+
+
+def test_boys_reference_fast_path_equals_faithful_loops(hostcheck):
+    """The table-driven reference Boys (cell lookup of the iteration count + Horner / Wallis)
+    must reproduce the faithful series / continued-fraction loops everywhere, including right
+    at the iteration-count steps, the branch switch x = m + 3/2 and the cell boundaries."""
+    assert hostcheck.hostcheck_ref_tables_ok() == 1  # at most one step per cell
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([
+        rng.uniform(0, 70, 60000), np.exp(rng.uniform(np.log(1e-9), np.log(5000), 20000)),
+        np.arange(0, 1200) / 16.0, np.nextafter(np.arange(1, 1200) / 16.0, 0),
+        np.arange(9) + 1.5, np.nextafter(np.arange(9) + 1.5, 0),
+        [0.0, 1e-9, 32, 36, np.nextafter(36, 0), 40, 48, 56, 64, np.nextafter(64, 0), 80, 128, 1e4]])
+    Ff, Fs = np.zeros(9), np.zeros(9)
     worst = 0.0
-    for j, x in enumerate(g["x"]):
-        hostcheck.hostcheck_boys(0, 8, float(x), F)
-        ref = g["F"][:9, j]
-        worst = max(worst, np.abs(F / ref - 1).max())
-    # same loops, same iteration counts; only the smooth wrapper differs: the reference forms
-    # exp(-x + a ln x - lgamma a) whose argument carries ~|arg| ulp of rounding noise
-    assert worst < 1e-13, worst
+    for x in xs:
+        hostcheck.hostcheck_boys(0, 8, float(x), Ff)
+        hostcheck.hostcheck_boys(2, 8, float(x), Fs)
+        worst = max(worst, np.abs(Ff / Fs - 1).max())
+    assert worst < 2e-14, worst
 
 
 def test_boys_exact_table(hostcheck, orc):
@@ -232,3 +253,15 @@ def test_gloo_world_size_2_allreduce(tmp_path):
                           "29611", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_reference_equals_exact_past_cut(hostcheck):
+    """primitive_quartet switches the reference flavour to the exact Boys path once x >=
+    ref_exact_from(L) (+0.5 margin): there the two functions agree to < 2e-15 relative."""
+    cut = {0: 14.0, 1: 16.0, 2: 20.0, 3: 22.0, 4: 24.0, 5: 24.0, 6: 30.0, 7: 36.0, 8: 36.0}
+    Fe, Fs = np.zeros(9), np.zeros(9)
+    for L, x0 in cut.items():
+        for x in np.concatenate([np.linspace(x0, x0 + 6, 300), np.linspace(x0 + 6, 200, 300)]):
+            hostcheck.hostcheck_boys(1, 8, float(x), Fe)
+            hostcheck.hostcheck_boys(2, 8, float(x), Fs)
+            assert np.abs(Fs[:L + 1] / Fe[:L + 1] - 1).max() < 4e-15, (L, x)
