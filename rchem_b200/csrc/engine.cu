@@ -211,6 +211,11 @@ struct rchem_basis {
   double* d_boys_ref = nullptr;  // reference-Boys step tables
   double *d_D = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // The tasks of one J/K (or tensor) build are independent kernels; they are spread over a
+  // few auxiliary streams so the tail of one launch overlaps the head of the next.
+  static constexpr int kAuxStreams = 6;
+  cudaStream_t aux[kAuxStreams] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kAuxStreams] = {};
   rchem_stats stats{};
 };
 
@@ -299,6 +304,11 @@ int ensure_ready(rchem_basis* h) {
   if (!h->external_stream) h->stream = h->own_stream;
   CUDA_OK(cudaEventCreate(&h->ev0));
   CUDA_OK(cudaEventCreate(&h->ev1));
+  CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < rchem_basis::kAuxStreams; ++i) {
+    CUDA_OK(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+  }
 
   // exact-Boys grid
   std::vector<double> table;
@@ -464,6 +474,16 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
   st = rchem_stats{};
   st.n_tasks = (int)h->tasks.size();
   CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+  // fork: the auxiliary streams wait for everything queued so far on the main stream
+  CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
+  for (int i = 0; i < rchem_basis::kAuxStreams; ++i)
+    CUDA_OK(cudaStreamWaitEvent(h->aux[i], h->ev_fork, 0));
+  int next_stream = 0;
+  auto pick_stream = [&]() {
+    cudaStream_t s = h->aux[next_stream];
+    next_stream = (next_stream + 1) % rchem_basis::kAuxStreams;
+    return s;
+  };
   for (const TaskTable& tt : h->tasks) {
     const Batch &B = h->batches[tt.bra], &K = h->batches[tt.ket];
     st.shell_quartets_all += tt.nquartets_all;
@@ -502,7 +522,7 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
       const long long nblocks = (nwarps + kWarpsPerBlock - 1) / kWarpsPerBlock;
       const long long mine = my_blocks(nblocks);
       if (mine > 0x7fffffffLL) return fail(RCHEM_ERR_TOO_LARGE, "task exceeds the grid limit");
-      CUDA_OK(fn(h->boys, mode, t, (unsigned)mine, h->stream));
+      CUDA_OK(fn(h->boys, mode, t, (unsigned)mine, pick_stream()));
       if (mine > 0) st.launches += 1;
       account((split ? tt.nquartets_light : tt.nquartets) * (double)mine / (double)nblocks);
     }
@@ -517,10 +537,15 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
       t.nblocks_heavy = tt.nblocks_heavy;
       const long long mine = my_blocks(tt.nblocks_heavy);
       if (mine > 0x7fffffffLL) return fail(RCHEM_ERR_TOO_LARGE, "task exceeds the grid limit");
-      CUDA_OK(bfn(h->boys, t, (unsigned)mine, tt.smem_bytes, h->stream));
+      CUDA_OK(bfn(h->boys, t, (unsigned)mine, tt.smem_bytes, pick_stream()));
       if (mine > 0) st.launches += 1;
       account((tt.nquartets - tt.nquartets_light) * (double)mine / (double)tt.nblocks_heavy);
     }
+  }
+  // join: the main stream waits for every auxiliary stream
+  for (int i = 0; i < rchem_basis::kAuxStreams; ++i) {
+    CUDA_OK(cudaEventRecord(h->ev_join[i], h->aux[i]));
+    CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_join[i], 0));
   }
   CUDA_OK(cudaEventRecord(h->ev1, h->stream));
   return RCHEM_OK;
@@ -609,6 +634,11 @@ void rchem_basis_destroy(rchem_basis* h) {
     cudaFree(h->d_boys); cudaFree(h->d_boys_ref); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (int i = 0; i < rchem_basis::kAuxStreams; ++i) {
+      if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+      if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
+    }
   }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;

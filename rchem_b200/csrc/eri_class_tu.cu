@@ -50,16 +50,27 @@ static cudaError_t launch_block(const EriTask& task, unsigned grid, size_t smem,
   return cudaGetLastError();
 }
 
+// The block kernel is only built for classes with <= 100 VRR targets: beyond that the
+// quartet itself dominates (and the register-bound kernel would not profit), so those
+// classes digest through the warp kernel.
+static constexpr bool kHasBlockKernel =
+    EriClass<RCHEM_LA, RCHEM_LB, RCHEM_LC, RCHEM_LD>::kTargets <= 100;
+
 cudaError_t RCHEM_CAT(launch_eri_block_, RCHEM_TAG)(int boys, const EriTask& task, unsigned grid,
                                                     size_t smem, cudaStream_t stream) {
   if (grid == 0) return cudaSuccess;
-  return boys == kBoysReference ? launch_block<kBoysReference>(task, grid, smem, stream)
-                                : launch_block<kBoysExact>(task, grid, smem, stream);
+  if constexpr (kHasBlockKernel) {
+    return boys == kBoysReference ? launch_block<kBoysReference>(task, grid, smem, stream)
+                                  : launch_block<kBoysExact>(task, grid, smem, stream);
+  } else {
+    return cudaErrorNotSupported;
+  }
 }
 
 EriBlockInfo RCHEM_CAT(block_info_, RCHEM_TAG)() {
   using Cfg = BlockCfg<RCHEM_LA, RCHEM_LB, RCHEM_LC, RCHEM_LD>;
-  return EriBlockInfo{Cfg::kThreadsBlk, Cfg::kKetsPerBlock};
+  if constexpr (kHasBlockKernel) return EriBlockInfo{Cfg::kThreadsBlk, Cfg::kKetsPerBlock};
+  return EriBlockInfo{0, 0};
 }
 
 }  // namespace rchem

@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
 // Dynamic shared memory: 2*(NA+NB)*N doubles + K2_bra primitive pairs.
 // ---------------------------------------------------------------------------------------
 #ifndef RCHEM_BLK_T_SMALL
-#define RCHEM_BLK_T_SMALL 384
+#define RCHEM_BLK_T_SMALL 512
 #endif
 #ifndef RCHEM_BLK_MINB_SMALL
 #define RCHEM_BLK_MINB_SMALL 2
