@@ -18,12 +18,12 @@
 // for x < 1/64, within 2^17 ulp of a step, or within 1e-10 of the branch switch x = m+3/2,
 // where the result depends on the exact rounding of x.
 #pragma once
-#include "eri_core.h"
+// (included from the middle of eri_core.h, after the Boys helpers it uses)
 
 namespace rchem {
 
 constexpr int kDeltaFineCells = 256;                    // x in [0, 4) at 1/64
-constexpr int kDeltaCells = kDeltaFineCells + 32 * 16;  // + x in [4, 36) at 1/16  -> 768
+constexpr int kDeltaCells = kDeltaFineCells + 33 * 16;  // + x in [4, 37) at 1/16  -> 784
 constexpr int kDeltaRowLen = 8;                         // 6 coefficients + 2 pad (32 bytes)
 constexpr int kDeltaMaxRows = kDeltaCells + 128;        // cells + steps, per order
 constexpr int kDeltaNearUlps = 1 << 17;

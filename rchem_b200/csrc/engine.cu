@@ -21,6 +21,7 @@
 #include "eri_kernel.cuh"
 #include "gen/eri_class_list.h"
 #include "pair_build.h"
+#include "boys_delta_build.h"
 
 namespace rchem {
 
@@ -209,6 +210,8 @@ struct rchem_basis {
   double tasks_tau = -1.0;
   double* d_boys = nullptr;      // exact-Boys grids, one per L
   double* d_boys_ref = nullptr;  // reference-Boys step tables
+  double* d_delta_thr = nullptr; // boys_delta.h tables
+  float* d_delta_rows = nullptr;
   double *d_D = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // The tasks of one J/K (or tensor) build are independent kernels; they are spread over a
@@ -282,7 +285,10 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
 void fill_common(const rchem_basis* h, EriTask* t) {
   std::memset(t, 0, sizeof(*t));
   t->N = h->N;
-  t->boys_table = h->d_boys;
+  t->boys.exact = h->d_boys;
+  t->boys.ref_steps = h->d_boys_ref;
+  t->boys.delta.thr = h->d_delta_thr;
+  t->boys.delta.rows = h->d_delta_rows;
   t->nranks = 1;
   for (int l = 0; l < 3; ++l)
     for (int k = 0; k < 6; ++k) t->compscale[l][k] = (l <= h->shells.lmax) ? h->shells.compscale[l][k] : 1.0;
@@ -320,6 +326,14 @@ int ensure_ready(rchem_basis* h) {
     return fail(RCHEM_ERR_CUDA, "internal: reference-Boys step table has a cell with two steps");
   CUDA_OK(cudaMalloc(&h->d_boys_ref, rtable.size() * sizeof(double)));
   CUDA_OK(cudaMemcpy(h->d_boys_ref, rtable.data(), rtable.size() * sizeof(double), cudaMemcpyHostToDevice));
+  std::vector<double> dthr;
+  std::vector<float> drows;
+  if (!build_boys_delta_tables(&dthr, &drows))
+    return fail(RCHEM_ERR_CUDA, "internal: reference-Boys correction table layout exceeded");
+  CUDA_OK(cudaMalloc(&h->d_delta_thr, dthr.size() * sizeof(double)));
+  CUDA_OK(cudaMalloc(&h->d_delta_rows, drows.size() * sizeof(float)));
+  CUDA_OK(cudaMemcpy(h->d_delta_thr, dthr.data(), dthr.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(h->d_delta_rows, drows.data(), drows.size() * sizeof(float), cudaMemcpyHostToDevice));
 
   // shell pairs -> batches keyed by (la, lb, K2); batch order = pair class, then K2 descending
   const auto& sh = h->shells.shells;
@@ -352,7 +366,7 @@ int ensure_ready(rchem_basis* h) {
     EriTask t;
     fill_common(h, &t);
     t.bra = t.ket = bt.view();
-    t.boys_table = h->d_boys + (size_t)(2 * (bt.la + bt.lb)) * kBoysTableLen;
+    t.boys.exact = h->d_boys + (size_t)(2 * (bt.la + bt.lb)) * kBoysTableLen;
     t.nwarps = (bt.npairs + 31) / 32;
     t.same = 1;
     t.Qout = dQ;
@@ -491,8 +505,7 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
     EriTask t = proto;
     t.bra = B.view();
     t.ket = K.view();
-    t.boys_table = h->d_boys + (size_t)(B.la + B.lb + K.la + K.lb) * kBoysTableLen;
-    t.boys_ref_table = h->d_boys_ref;
+    t.boys.exact = h->d_boys + (size_t)(B.la + B.lb + K.la + K.lb) * kBoysTableLen;
     t.nq = tt.d_nq;
     t.same = tt.bra == tt.ket;
     t.rank = rank;
@@ -631,7 +644,7 @@ void rchem_basis_destroy(rchem_basis* h) {
     for (Batch& bt : h->batches) {
       cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_idx); cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
     }
-    cudaFree(h->d_boys); cudaFree(h->d_boys_ref); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK);
+    cudaFree(h->d_boys); cudaFree(h->d_boys_ref); cudaFree(h->d_delta_thr); cudaFree(h->d_delta_rows); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);

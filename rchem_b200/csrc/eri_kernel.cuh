@@ -60,8 +60,7 @@ struct EriTask {
   int nheavy;
   double* I;                     // [N]^4 dense tensor                    kModeTensor
   double* Qout;                  // [bra.npairs] Schwarz bounds           kModeSchwarz
-  const double* boys_table;      // exact-Boys grid of this class's L (eri_core.h)
-  const double* boys_ref_table;  // reference-Boys step tables (eri_core.h)
+  BoysTabs boys;                 // Boys tables (exact grid of this class's L, reference tables)
   double compscale[3][6];        // per-l component norm ratios (basis_model.h)
 };
 
@@ -124,12 +123,10 @@ __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const B
     const PrimPair pk = load_prim(t.ket, kk, q);
     for (int kb = 0; kb < K2b; ++kb) {
       if (BRA_SMEM) {
-        primitive_quartet<C, BOYS>(s_bra[kb], pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys_table,
-                                   t.boys_ref_table, acc);
+        primitive_quartet<C, BOYS>(s_bra[kb], pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys, acc);
       } else {
         const PrimPair pb = load_prim(t.bra, kb, p);
-        primitive_quartet<C, BOYS>(pb, pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys_table,
-                                   t.boys_ref_table, acc);
+        primitive_quartet<C, BOYS>(pb, pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys, acc);
       }
     }
   }

@@ -11,6 +11,7 @@
 #include "../rchem_b200/csrc/basis_model.h"
 #include "../rchem_b200/csrc/eri_core.h"
 #include "../rchem_b200/csrc/pair_build.h"
+#include "../rchem_b200/csrc/boys_delta_build.h"
 #include "../rchem_b200/csrc/gen/eri_class_list.h"
 
 namespace rchem {
@@ -38,7 +39,7 @@ namespace rchem {
 
 template <class C, int BOYS>
 void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const Shell& Cc,
-                   const Shell& D, const double* table, const double* rtable, double* out) {
+                   const Shell& D, const BoysTabs& tabs, double* out) {
   std::vector<PrimPair> bra, ket;
   build_prim_pairs(A, B, &bra);
   build_prim_pairs(Cc, D, &ket);
@@ -46,7 +47,7 @@ void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const She
   for (const PrimPair& k : ket)
     for (const PrimPair& b : bra)
       primitive_quartet<C, BOYS>(b, k, A.ctr[0], A.ctr[1], A.ctr[2], Cc.ctr[0], Cc.ctr[1],
-                                 Cc.ctr[2], table, rtable, acc.data());
+                                 Cc.ctr[2], tabs, acc.data());
   C::hrr(acc.data(), A.ctr[0] - B.ctr[0], A.ctr[1] - B.ctr[1], A.ctr[2] - B.ctr[2],
          Cc.ctr[0] - D.ctr[0], Cc.ctr[1] - D.ctr[1], Cc.ctr[2] - D.ctr[2], out);
   const int na = ncart(A.l), nb = ncart(B.l), nc = ncart(Cc.l), nd = ncart(D.l);
@@ -60,6 +61,29 @@ void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const She
 }  // namespace rchem
 
 using namespace rchem;
+
+struct AllTabs {
+  std::vector<double> exact, steps, dthr;
+  std::vector<float> drows;
+  bool delta_ok = false;
+  BoysTabs tabs(int L) const {
+    BoysTabs t;
+    t.exact = exact.data() + (size_t)L * kBoysTableLen;
+    t.ref_steps = steps.data();
+    t.delta.thr = dthr.data();
+    t.delta.rows = drows.data();
+    return t;
+  }
+};
+static const AllTabs& all_tabs() {
+  static AllTabs T;
+  if (T.exact.empty()) {
+    build_boys_tables(&T.exact);
+    build_boys_ref_tables(&T.steps);
+    T.delta_ok = build_boys_delta_tables(&T.dthr, &T.drows);
+  }
+  return T;
+}
 
 static Basis from_flat(int n, const double* origins, const int32_t* powers,
                        const int32_t* prim_offset, const double* exps, const double* coefs,
@@ -106,17 +130,16 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
   ShellSet ss;
   std::string err;
   if (!group_shells(b, &ss, &err)) return -1;
-  static std::vector<double> table, rtable;
-  if (table.empty()) { build_boys_tables(&table); build_boys_ref_tables(&rtable); }
+  const AllTabs& T = all_tabs();
   const Shell &A = ss.shells[sa], &B = ss.shells[sb], &C = ss.shells[sc], &D = ss.shells[sd];
 #define X(la, lb, lc, ld, tag)                                                              \
   if (A.l == la && B.l == lb && C.l == lc && D.l == ld) {                                   \
     if (boys == kBoysReference)                                                             \
-      shell_quartet<EriClass<la, lb, lc, ld>, kBoysReference>(                              \
-          ss, A, B, C, D, table.data() + (la + lb + lc + ld) * kBoysTableLen, rtable.data(), out); \
+      shell_quartet<EriClass<la, lb, lc, ld>, kBoysReference>(ss, A, B, C, D,                \
+                                                              T.tabs(la + lb + lc + ld), out); \
     else                                                                                    \
-      shell_quartet<EriClass<la, lb, lc, ld>, kBoysExact>(                                  \
-          ss, A, B, C, D, table.data() + (la + lb + lc + ld) * kBoysTableLen, rtable.data(), out); \
+      shell_quartet<EriClass<la, lb, lc, ld>, kBoysExact>(ss, A, B, C, D,                    \
+                                                          T.tabs(la + lb + lc + ld), out);  \
     return EriClass<la, lb, lc, ld>::kOut;                                                  \
   }
   RCHEM_ERI_CLASSES(X)
@@ -126,28 +149,42 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
 
 extern "C" int hostcheck_ref_tables_ok() {
   std::vector<double> t;
-  return build_boys_ref_tables(&t) ? 1 : 0;
+  return (build_boys_ref_tables(&t) ? 1 : 0) + (all_tabs().delta_ok ? 2 : 0);
 }
 
-// boys: 0 = fast reference path, 1 = exact, 2 = faithful reference loops
+// boys: 0 = reference via step tables (Horner / Wallis), 1 = exact, 2 = faithful reference
+// loops, 3 = reference as exact minus tabulated correction (the path the kernels use)
 extern "C" void hostcheck_boys(int boys, int L, double x, double* F) {
-  static std::vector<double> table, rtable;
-  if (table.empty()) { build_boys_tables(&table); build_boys_ref_tables(&rtable); }
+  const AllTabs& T = all_tabs();
   if (boys == 2) { boys_reference_faithful<8>(x, F); return; }
-  // L <= 8
+  if (boys == 3) {
+    double ex = 0.0;
+    auto exact_x = [&]() { return x; };
+    switch (L) {
+      case 0: boys_exact<0, true>(x, T.tabs(0).exact, F, &ex);
+              if (x < ref_exact_from(0) + 0.5) boys_reference_from_exact<0>(x, ex, T.tabs(0).delta, exact_x, F); break;
+      case 2: boys_exact<2, true>(x, T.tabs(2).exact, F, &ex);
+              if (x < ref_exact_from(2) + 0.5) boys_reference_from_exact<2>(x, ex, T.tabs(2).delta, exact_x, F); break;
+      case 4: boys_exact<4, true>(x, T.tabs(4).exact, F, &ex);
+              if (x < ref_exact_from(4) + 0.5) boys_reference_from_exact<4>(x, ex, T.tabs(4).delta, exact_x, F); break;
+      default: boys_exact<8, true>(x, T.tabs(8).exact, F, &ex);
+              if (x < ref_exact_from(8) + 0.5) boys_reference_from_exact<8>(x, ex, T.tabs(8).delta, exact_x, F); break;
+    }
+    return;
+  }
   if (boys == kBoysReference) {
     switch (L) {
-      case 0: boys_reference<0>(x, rtable.data(), F); break;
-      case 2: boys_reference<2>(x, rtable.data(), F); break;
-      case 4: boys_reference<4>(x, rtable.data(), F); break;
-      default: boys_reference<8>(x, rtable.data(), F); break;
+      case 0: boys_reference<0>(x, T.steps.data(), F); break;
+      case 2: boys_reference<2>(x, T.steps.data(), F); break;
+      case 4: boys_reference<4>(x, T.steps.data(), F); break;
+      default: boys_reference<8>(x, T.steps.data(), F); break;
     }
   } else {
     switch (L) {
-      case 0: boys_exact<0>(x, table.data(), F); break;
-      case 2: boys_exact<2>(x, table.data() + 2 * kBoysTableLen, F); break;
-      case 4: boys_exact<4>(x, table.data() + 4 * kBoysTableLen, F); break;
-      default: boys_exact<8>(x, table.data() + 8 * kBoysTableLen, F); break;
+      case 0: boys_exact<0>(x, T.tabs(0).exact, F); break;
+      case 2: boys_exact<2>(x, T.tabs(2).exact, F); break;
+      case 4: boys_exact<4>(x, T.tabs(4).exact, F); break;
+      default: boys_exact<8>(x, T.tabs(8).exact, F); break;
     }
   }
 }

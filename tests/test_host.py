@@ -176,20 +176,30 @@ def test_boys_reference_fast_path_equals_faithful_loops(hostcheck):
     """The table-driven reference Boys (cell lookup of the iteration count + Horner / Wallis)
     must reproduce the faithful series / continued-fraction loops everywhere, including right
     at the iteration-count steps, the branch switch x = m + 3/2 and the cell boundaries."""
-    assert hostcheck.hostcheck_ref_tables_ok() == 1  # at most one step per cell
+    assert hostcheck.hostcheck_ref_tables_ok() == 3  # both table sets: at most one step per cell
     rng = np.random.default_rng(0)
     xs = np.concatenate([
         rng.uniform(0, 70, 60000), np.exp(rng.uniform(np.log(1e-9), np.log(5000), 20000)),
         np.arange(0, 1200) / 16.0, np.nextafter(np.arange(1, 1200) / 16.0, 0),
         np.arange(9) + 1.5, np.nextafter(np.arange(9) + 1.5, 0),
         [0.0, 1e-9, 32, 36, np.nextafter(36, 0), 40, 48, 56, 64, np.nextafter(64, 0), 80, 128, 1e4]])
-    Ff, Fs = np.zeros(9), np.zeros(9)
-    worst = 0.0
+    xs = np.concatenate([xs, np.arange(0, 2400) / 64.0, np.nextafter(np.arange(1, 2400) / 64.0, 0),
+                         (np.arange(9) + 1.5) * (1 + 1e-12), (np.arange(9) + 1.5) * (1 - 1e-12)])
+    Ff, Fd, Fs = np.zeros(9), np.zeros(9), np.zeros(9)
+    worst, worst_d = 0.0, 0.0
     for x in xs:
-        hostcheck.hostcheck_boys(0, 8, float(x), Ff)
-        hostcheck.hostcheck_boys(2, 8, float(x), Fs)
+        hostcheck.hostcheck_boys(0, 8, float(x), Ff)   # step tables + Horner / Wallis
+        hostcheck.hostcheck_boys(3, 8, float(x), Fd)   # exact minus tabulated correction (kernels)
+        hostcheck.hostcheck_boys(2, 8, float(x), Fs)   # faithful loops
         worst = max(worst, np.abs(Ff / Fs - 1).max())
+        worst_d = max(worst_d, np.abs(Fd / Fs - 1).max())
     assert worst < 2e-14, worst
+    assert worst_d < 2e-14, worst_d
+    for L in (0, 2, 4):  # the lower-L instantiations share the tables
+        for x in xs[::11]:
+            hostcheck.hostcheck_boys(3, L, float(x), Fd)
+            hostcheck.hostcheck_boys(2, 8, float(x), Fs)
+            assert np.abs(Fd[:L + 1] / Fs[:L + 1] - 1).max() < 2e-14, (L, x)
 
 
 def test_boys_exact_table(hostcheck, orc):
@@ -258,10 +268,10 @@ def test_gloo_world_size_2_allreduce(tmp_path):
 def test_reference_equals_exact_past_cut(hostcheck):
     """primitive_quartet switches the reference flavour to the exact Boys path once x >=
     ref_exact_from(L) (+0.5 margin): there the two functions agree to < 2e-15 relative."""
-    cut = {0: 14.0, 1: 16.0, 2: 20.0, 3: 22.0, 4: 24.0, 5: 24.0, 6: 30.0, 7: 36.0, 8: 36.0}
+    cut = {0: 14.0, 1: 16.0, 2: 18.0, 3: 20.0, 4: 20.0, 5: 22.0, 6: 26.0, 7: 30.0, 8: 36.0}
     Fe, Fs = np.zeros(9), np.zeros(9)
-    for L, x0 in cut.items():
+    for m, x0 in cut.items():  # per order (eri_core.h ref_exact_from_order)
         for x in np.concatenate([np.linspace(x0, x0 + 6, 300), np.linspace(x0 + 6, 200, 300)]):
             hostcheck.hostcheck_boys(1, 8, float(x), Fe)
             hostcheck.hostcheck_boys(2, 8, float(x), Fs)
-            assert np.abs(Fs[:L + 1] / Fe[:L + 1] - 1).max() < 4e-15, (L, x)
+            assert abs(Fs[m] / Fe[m] - 1) < 4e-15, (m, x)
