@@ -209,7 +209,6 @@ struct rchem_basis {
   std::vector<TaskTable> tasks;
   double tasks_tau = -1.0;
   double* d_boys = nullptr;      // exact-Boys grids, one per L
-  double* d_boys_ref = nullptr;  // reference-Boys step tables
   double* d_delta_thr = nullptr; // boys_delta.h tables
   float* d_delta_rows = nullptr;
   double *d_D = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
@@ -286,7 +285,6 @@ void fill_common(const rchem_basis* h, EriTask* t) {
   std::memset(t, 0, sizeof(*t));
   t->N = h->N;
   t->boys.exact = h->d_boys;
-  t->boys.ref_steps = h->d_boys_ref;
   t->boys.delta.thr = h->d_delta_thr;
   t->boys.delta.rows = h->d_delta_rows;
   t->nranks = 1;
@@ -321,11 +319,6 @@ int ensure_ready(rchem_basis* h) {
   build_boys_tables(&table);
   CUDA_OK(cudaMalloc(&h->d_boys, table.size() * sizeof(double)));
   CUDA_OK(cudaMemcpy(h->d_boys, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
-  std::vector<double> rtable;
-  if (!build_boys_ref_tables(&rtable))
-    return fail(RCHEM_ERR_CUDA, "internal: reference-Boys step table has a cell with two steps");
-  CUDA_OK(cudaMalloc(&h->d_boys_ref, rtable.size() * sizeof(double)));
-  CUDA_OK(cudaMemcpy(h->d_boys_ref, rtable.data(), rtable.size() * sizeof(double), cudaMemcpyHostToDevice));
   std::vector<double> dthr;
   std::vector<float> drows;
   if (!build_boys_delta_tables(&dthr, &drows))
@@ -644,7 +637,7 @@ void rchem_basis_destroy(rchem_basis* h) {
     for (Batch& bt : h->batches) {
       cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_idx); cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
     }
-    cudaFree(h->d_boys); cudaFree(h->d_boys_ref); cudaFree(h->d_delta_thr); cudaFree(h->d_delta_rows); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK);
+    cudaFree(h->d_boys); cudaFree(h->d_delta_thr); cudaFree(h->d_delta_rows); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);

@@ -67,9 +67,8 @@ inline void build_boys_tables(std::vector<double>* tables) {
   }
 }
 
-// Tables for the fast reference-Boys path (eri_core.h boys_reference): for every order m the
-// iteration count of the reference's series / continued-fraction loop as a step function of
-// x, found by bisection over the FAITHFUL loops (boys_reference_order).
+// Iteration count of the reference's series / continued-fraction loop as a step function of
+// x (for the tables of boys_delta.h), from the FAITHFUL loops (boys_reference_order).
 inline int ref_iterations(int m, double x) {
   int n = 0;
   boys_reference_order(m, x, 0.0, 0.0, &n);
@@ -84,54 +83,6 @@ inline double ref_step(int m, double lo, double hi, int n_lo) {
     if (ref_iterations(m, mid) == n_lo) lo = mid; else hi = mid;
   }
   return hi;
-}
-
-inline double ref_encode(double thr, int n) {
-  long long b;
-  __builtin_memcpy(&b, &thr, 8);
-  b = (b & ~31LL) | (long long)(n & 31);
-  double r;
-  __builtin_memcpy(&r, &b, 8);
-  return r;
-}
-
-// Returns false if some cell holds more than one step (the layout assumes at most one).
-inline bool build_boys_ref_tables(std::vector<double>* tab) {
-  tab->assign(kRefTableLen, 0.0);
-  bool ok = true;
-  for (int m = 0; m <= kRefMaxM; ++m) {
-    double* t = tab->data() + (size_t)m * kRefStride;
-    const double a = m + 0.5;
-    for (int c = 0; c < kRefCells; ++c) {
-      double lo, hi;
-      if (c < kRefLinCells) {
-        lo = c / 16.0;
-        hi = (c + 1) / 16.0;
-      } else {  // quarter-octave cells from 32: [32*2^(j/4-ish)) by exponent + 2 mantissa bits
-        const int j = c - kRefLinCells;
-        lo = std::ldexp(1.0 + 0.25 * (j % 4), 5 + j / 4);
-        hi = std::ldexp(1.0 + 0.25 * (j % 4 + 1), 5 + j / 4);
-      }
-      hi = std::nextafter(hi, 0.0);
-      if (c == 0) { t[c] = ref_encode(1e300, 0); continue; }  // cell 0 uses the faithful loop
-      const int n_lo = ref_iterations(m, lo), n_hi = ref_iterations(m, hi);
-      const bool series = lo < a + 1.0;
-      if (n_lo == n_hi) {
-        t[c] = ref_encode(1e300, n_lo);
-      } else {
-        if (n_hi != n_lo + (series ? 1 : -1) || n_lo > 30) ok = false;
-        t[c] = ref_encode(ref_step(m, lo, hi, n_lo), n_lo);
-      }
-    }
-    long double prod = 1.0L;
-    for (int k = 0; k < kRefCoefs; ++k) {
-      prod *= (a + k);
-      t[kRefCells + k] = (double)(1.0L / prod);           // 1/((a)(a+1)..(a+k))
-      t[kRefCells + kRefCoefs + k] = -(double)k * (k - a);  // a_j = -j (j - a)
-    }
-  }
-  for (int c = 0; c <= kRefLinCells; ++c) (*tab)[kRefExpoOffset + c] = (double)expl(-(long double)c / 16.0L);
-  return ok;
 }
 
 }  // namespace rchem

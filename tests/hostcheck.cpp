@@ -63,13 +63,12 @@ void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const She
 using namespace rchem;
 
 struct AllTabs {
-  std::vector<double> exact, steps, dthr;
+  std::vector<double> exact, dthr;
   std::vector<float> drows;
   bool delta_ok = false;
   BoysTabs tabs(int L) const {
     BoysTabs t;
     t.exact = exact.data() + (size_t)L * kBoysTableLen;
-    t.ref_steps = steps.data();
     t.delta.thr = dthr.data();
     t.delta.rows = drows.data();
     return t;
@@ -79,7 +78,6 @@ static const AllTabs& all_tabs() {
   static AllTabs T;
   if (T.exact.empty()) {
     build_boys_tables(&T.exact);
-    build_boys_ref_tables(&T.steps);
     T.delta_ok = build_boys_delta_tables(&T.dthr, &T.drows);
   }
   return T;
@@ -148,16 +146,15 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
 }
 
 extern "C" int hostcheck_ref_tables_ok() {
-  std::vector<double> t;
-  return (build_boys_ref_tables(&t) ? 1 : 0) + (all_tabs().delta_ok ? 2 : 0);
+  return all_tabs().delta_ok ? 1 : 0;
 }
 
-// boys: 0 = reference via step tables (Horner / Wallis), 1 = exact, 2 = faithful reference
-// loops, 3 = reference as exact minus tabulated correction (the path the kernels use)
+// boys: 0 (or 3) = reference as exact minus tabulated correction (the path the kernels use),
+// 1 = exact, 2 = faithful reference loops
 extern "C" void hostcheck_boys(int boys, int L, double x, double* F) {
   const AllTabs& T = all_tabs();
   if (boys == 2) { boys_reference_faithful<8>(x, F); return; }
-  if (boys == 3) {
+  if (boys == 3 || boys == kBoysReference) {
     double ex = 0.0;
     auto exact_x = [&]() { return x; };
     switch (L) {
@@ -172,14 +169,7 @@ extern "C" void hostcheck_boys(int boys, int L, double x, double* F) {
     }
     return;
   }
-  if (boys == kBoysReference) {
-    switch (L) {
-      case 0: boys_reference<0>(x, T.steps.data(), F); break;
-      case 2: boys_reference<2>(x, T.steps.data(), F); break;
-      case 4: boys_reference<4>(x, T.steps.data(), F); break;
-      default: boys_reference<8>(x, T.steps.data(), F); break;
-    }
-  } else {
+  {
     switch (L) {
       case 0: boys_exact<0>(x, T.tabs(0).exact, F); break;
       case 2: boys_exact<2>(x, T.tabs(2).exact, F); break;

@@ -281,3 +281,65 @@ def test_device_api_and_rank_partition(rc, geo):
     assert np.abs(JK[0].cpu().numpy() - J).max() < 1e-12
     assert np.abs(JK[1].cpu().numpy() - K).max() < 1e-12
     b.use_own_stream()
+
+
+# ---- the caller of the hot path: the reference's RHF loop (rchem.rs:40-89) -------------------------------
+def test_rhf_water_crawford_energy(rc, orc, geo):
+    """SCF driven exactly like src/bin/rchem.rs (core guess, symmetric orthogonalisation,
+    F = H + 2J - K, nocc = 5, |dE| < 1e-11) with J/K from the GPU path.  One-electron matrices
+    come from the reference's own C kernels (test infrastructure).  SURVEY section 6: converged
+    E_elec = -82.944446488 with libpyquante2 integrals (Crawford: -82.944446990)."""
+    import ctypes as C
+
+    ref = orc.ref_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref not available")
+    d, i = C.c_double, C.c_int
+    for fn in (ref.overlap, ref.kinetic):
+        fn.restype = d
+        fn.argtypes = [d, i, i, i, d, d, d, d, i, i, i, d, d, d]
+    ref.nuclear_attraction.restype = d
+    ref.nuclear_attraction.argtypes = [d, d, d, d, i, i, i, d, d, d, d, d, i, i, i, d, d, d, d]
+    z, x = geo.molecule(geo.WATER_CRAWFORD)
+    ob = orc.make_basis(z, x, "STO-3G")
+    n = ob.n
+    S, T, V = np.zeros((n, n)), np.zeros((n, n)), np.zeros((n, n))
+    for mu in range(n):
+        for nu in range(n):
+            for p in range(ob.prim_offset[mu], ob.prim_offset[mu + 1]):
+                for q in range(ob.prim_offset[nu], ob.prim_offset[nu + 1]):
+                    cc = ob.coefs[p] * ob.coefs[q]
+                    a = (float(ob.exps[p]), *map(int, ob.powers[mu]), *map(float, ob.origins[mu]))
+                    b = (float(ob.exps[q]), *map(int, ob.powers[nu]), *map(float, ob.origins[nu]))
+                    nn = ob.norms[p] * ob.norms[q]
+                    S[mu, nu] += cc * nn * ref.overlap(*a, *b)
+                    T[mu, nu] += cc * nn * ref.kinetic(*a, *b)
+                    for zc, xc in zip(z, x):
+                        V[mu, nu] += cc * float(zc) * ref.nuclear_attraction(
+                            *map(float, ob.origins[mu]), float(ob.norms[p]), *map(int, ob.powers[mu]),
+                            float(ob.exps[p]), *map(float, ob.origins[nu]), float(ob.norms[q]),
+                            *map(int, ob.powers[nu]), float(ob.exps[q]), *map(float, xc))
+    H = T + V
+    w, U = np.linalg.eigh(S)
+    X = U @ np.diag(w ** -0.5) @ U.T
+    basis = rc.Basis.new(z, x, "STO-3G")
+
+    def density(F):
+        _, Cp = np.linalg.eigh(X.T @ F @ X)
+        Cm = X @ Cp
+        return Cm[:, :5] @ Cm[:, :5].T
+
+    D = density(H)
+    e_new = ((H + H) * D).sum()
+    assert abs(e_new - (-125.842076851)) < 5e-8  # core-guess energy, SURVEY section 6
+    J, K = np.zeros((n, n)), np.zeros((n, n))
+    for it in range(200):
+        rc.JK_direct(J, K, basis, np.ascontiguousarray((D + D.T) / 2))
+        F = H + 2.0 * J - K
+        D = density(F)
+        e_old, e_new = e_new, ((H + F) * D).sum()
+        if abs(e_new - e_old) < 1e-11:
+            break
+    assert it < 100
+    assert abs(e_new - (-82.944446488)) < 5e-8
+    assert abs(e_new - (-82.944446990)) < 1e-6  # Crawford's published value

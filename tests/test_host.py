@@ -173,10 +173,11 @@ def test_boys_reference_restatement_bitwise_iterations(hostcheck, orc):
 
 
 def test_boys_reference_fast_path_equals_faithful_loops(hostcheck):
-    """The table-driven reference Boys (cell lookup of the iteration count + Horner / Wallis)
-    must reproduce the faithful series / continued-fraction loops everywhere, including right
-    at the iteration-count steps, the branch switch x = m + 3/2 and the cell boundaries."""
-    assert hostcheck.hostcheck_ref_tables_ok() == 3  # both table sets: at most one step per cell
+    """The table-driven reference Boys (converged Boys minus the tabulated truncation error
+    of Fgamma, boys_delta.h) must reproduce the faithful series / continued-fraction loops
+    everywhere, including right at the iteration-count steps, the branch switch x = m + 3/2
+    and the cell boundaries."""
+    assert hostcheck.hostcheck_ref_tables_ok() == 1  # at most one step per cell, layout limits ok
     rng = np.random.default_rng(0)
     xs = np.concatenate([
         rng.uniform(0, 70, 60000), np.exp(rng.uniform(np.log(1e-9), np.log(5000), 20000)),
@@ -185,15 +186,12 @@ def test_boys_reference_fast_path_equals_faithful_loops(hostcheck):
         [0.0, 1e-9, 32, 36, np.nextafter(36, 0), 40, 48, 56, 64, np.nextafter(64, 0), 80, 128, 1e4]])
     xs = np.concatenate([xs, np.arange(0, 2400) / 64.0, np.nextafter(np.arange(1, 2400) / 64.0, 0),
                          (np.arange(9) + 1.5) * (1 + 1e-12), (np.arange(9) + 1.5) * (1 - 1e-12)])
-    Ff, Fd, Fs = np.zeros(9), np.zeros(9), np.zeros(9)
-    worst, worst_d = 0.0, 0.0
+    Fd, Fs = np.zeros(9), np.zeros(9)
+    worst_d = 0.0
     for x in xs:
-        hostcheck.hostcheck_boys(0, 8, float(x), Ff)   # step tables + Horner / Wallis
         hostcheck.hostcheck_boys(3, 8, float(x), Fd)   # exact minus tabulated correction (kernels)
         hostcheck.hostcheck_boys(2, 8, float(x), Fs)   # faithful loops
-        worst = max(worst, np.abs(Ff / Fs - 1).max())
         worst_d = max(worst_d, np.abs(Fd / Fs - 1).max())
-    assert worst < 2e-14, worst
     assert worst_d < 2e-14, worst_d
     for L in (0, 2, 4):  # the lower-L instantiations share the tables
         for x in xs[::11]:
