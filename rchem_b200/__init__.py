@@ -167,8 +167,11 @@ class Basis:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            _lib.rchem_basis_destroy(h)
+        if h and _lib is not None:  # module globals may already be gone at interpreter exit
+            try:
+                _lib.rchem_basis_destroy(h)
+            except Exception:
+                pass
 
     # --- data model access -----------------------------------------------------------
     def export(self):

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -438,11 +439,17 @@ int ensure_tasks(rchem_basis* h) {
       tt.smem_bytes = (size_t)2 * (ncart(B.la) + ncart(B.lb)) * h->N * sizeof(double) +
                       (size_t)B.K2 * sizeof(PrimPair);
       const bool rows_fit = tt.smem_bytes <= kMaxBlockSmem && info.threads > 0;
+      // a bra pair is "heavy" when its ket prefix fills the block kernel's threads at least
+      // kHeavyPasses times (the last, partial pass of a block idles most of its warps)
+      static const int kHeavyPasses = [] {
+        const char* e = std::getenv("RCHEM_HEAVY_PASSES");
+        return e ? std::max(1, atoi(e)) : 1;
+      }();
       std::vector<int> nq_light(B.npairs), hp;
       std::vector<long long> prefix_light(B.npairs + 1, 0), hblk(1, 0);
       for (int p = 0; p < B.npairs; ++p) {
         const int cut = tt.h_nq[p];
-        const bool heavy = rows_fit && cut >= info.threads;
+        const bool heavy = rows_fit && cut >= kHeavyPasses * info.threads;
         nq_light[p] = heavy ? 0 : cut;
         prefix_light[p + 1] = prefix_light[p] + (nq_light[p] + 31) / 32;
         if (heavy) {
