@@ -151,6 +151,36 @@ __global__ void finalize_k_kernel(const double* __restrict__ Kh, double* __restr
   K[idx] = Kh[idx] + Kh[j * N + i];
 }
 
+// Dense-tensor completion (build_I, basis.rs:451-454 plus the bra<->ket swap): the ERI kernels
+// write each unique integral once, at its canonical position (stored orientation of both
+// shell pairs, bra pair >= ket pair in kernel order).  This kernel fills every other element
+// from its canonical image, writing coalesced along the last index.
+//   fn_shell[i]      : shell of function i
+//   pair_key[s*ns+t] : kernel-order rank of shell pair {s,t} (batch << 32 | position)
+//   pair_fwd[s*ns+t] : 1 when the pair is stored as (A=s, B=t)
+__global__ void tensor_fill_kernel(double* __restrict__ I, int N, int ns,
+                                   const int* __restrict__ fn_shell,
+                                   const long long* __restrict__ pair_key,
+                                   const unsigned char* __restrict__ pair_fwd) {
+  const int ij = blockIdx.x, kl = blockIdx.y * blockDim.x + threadIdx.x;
+  if (kl >= N * N) return;
+  const int i = ij / N, j = ij % N, k = kl / N, l = kl % N;
+  const int si = fn_shell[i], sj = fn_shell[j], sk = fn_shell[k], sl = fn_shell[l];
+  const long long kp = pair_key[si * ns + sj], kq = pair_key[sk * ns + sl];
+  // stored orientation of each pair; inside a diagonal shell pair (both orders were computed)
+  // keep the order with the larger first function so the tensor is bitwise symmetric
+  const bool fp = si == sj ? i >= j : (bool)pair_fwd[si * ns + sj];
+  const bool fq = sk == sl ? k >= l : (bool)pair_fwd[sk * ns + sl];
+  const size_t ci = fp ? i : j, cj = fp ? j : i, ck = fq ? k : l, cl = fq ? l : k;
+  const size_t n = (size_t)N;
+  // inside one shell pair (kp == kq) both (ab|cd) and (cd|ab) were computed; keep the one with
+  // the larger leading function pair so the tensor is bitwise symmetric under bra <-> ket
+  const bool bra_first = kp > kq || (kp == kq && ci * n + cj >= ck * n + cl);
+  const size_t src = bra_first ? ((ci * n + cj) * n + ck) * n + cl : ((ck * n + cl) * n + ci) * n + cj;
+  const size_t dst = (((size_t)i * n + j) * n + k) * n + l;
+  if (src != dst) I[dst] = I[src];
+}
+
 // JK_inmem (basis.rs:462-484) in ONE pass over the tensor: element I[i][j][k][l] feeds
 // J[i][j] (with D[k][l]) and K[i][k] (with D[j][l]).  One block per (i,j) row of N^2 values;
 // one warp per k sums over l.  HBM-bound: 8 N^4 bytes read once.
@@ -213,6 +243,10 @@ struct rchem_basis {
   double* d_delta_thr = nullptr; // boys_delta.h tables
   float* d_delta_rows = nullptr;
   double *d_D = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
+  // maps for tensor_fill_kernel
+  int* d_fn_shell = nullptr;
+  long long* d_pair_key = nullptr;
+  unsigned char* d_pair_fwd = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // The tasks of one J/K (or tensor) build are independent kernels; they are spread over a
   // few auxiliary streams so the tail of one launch overlaps the head of the next.
@@ -383,6 +417,30 @@ int ensure_ready(rchem_basis* h) {
   CUDA_OK(cudaMalloc(&h->d_D, nn * sizeof(double)));
   CUDA_OK(cudaMalloc(&h->d_Kh, nn * sizeof(double)));
   CUDA_OK(cudaMalloc(&h->d_JK, 2 * nn * sizeof(double)));
+  {  // maps for the dense-tensor completion
+    const int ns = (int)sh.size();
+    std::vector<int> fn_shell(h->N);
+    for (int s = 0; s < ns; ++s)
+      for (int k = 0; k < ncart(sh[s].l); ++k) fn_shell[sh[s].bf0 + k] = s;
+    std::vector<long long> key((size_t)ns * ns, 0);
+    std::vector<unsigned char> fwd((size_t)ns * ns, 0);
+    for (size_t bi = 0; bi < h->batches.size(); ++bi) {
+      const Batch& bt = h->batches[bi];
+      for (int p = 0; p < bt.npairs; ++p) {
+        const int a = bt.shA[p], b = bt.shB[p];
+        const long long kk = ((long long)bi << 32) | (long long)p;
+        key[(size_t)a * ns + b] = key[(size_t)b * ns + a] = kk;
+        fwd[(size_t)a * ns + b] = 1;
+        if (a != b) fwd[(size_t)b * ns + a] = 0;
+      }
+    }
+    CUDA_OK(cudaMalloc(&h->d_fn_shell, fn_shell.size() * sizeof(int)));
+    CUDA_OK(cudaMalloc(&h->d_pair_key, key.size() * sizeof(long long)));
+    CUDA_OK(cudaMalloc(&h->d_pair_fwd, fwd.size()));
+    CUDA_OK(cudaMemcpy(h->d_fn_shell, fn_shell.data(), fn_shell.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->d_pair_key, key.data(), key.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->d_pair_fwd, fwd.data(), fwd.size(), cudaMemcpyHostToDevice));
+  }
   h->ready = true;
   return RCHEM_OK;
 }
@@ -645,6 +703,7 @@ void rchem_basis_destroy(rchem_basis* h) {
       cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_idx); cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
     }
     cudaFree(h->d_boys); cudaFree(h->d_delta_thr); cudaFree(h->d_delta_rows); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK);
+    cudaFree(h->d_fn_shell); cudaFree(h->d_pair_key); cudaFree(h->d_pair_fwd);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -813,11 +872,22 @@ int rchem_build_I_device(rchem_basis* h, double* I_dev) {
   rc = ensure_tasks(h);
   if (rc) return rc;
   const size_t n4 = (size_t)h->N * h->N * h->N * h->N;
-  CUDA_OK(cudaMemsetAsync(I_dev, 0, n4 * sizeof(double), h->stream));
+  // screened-out quartets must read as zero; without screening every canonical element is
+  // written by the ERI kernels and every other element by the fill kernel
+  if (h->tau > 0.0) CUDA_OK(cudaMemsetAsync(I_dev, 0, n4 * sizeof(double), h->stream));
   EriTask proto;
   fill_common(h, &proto);
   proto.I = I_dev;
-  return run_tasks(h, kModeTensor, proto, 0, 1);
+  rc = run_tasks(h, kModeTensor, proto, 0, 1);
+  if (rc) return rc;
+  const unsigned nn = (unsigned)(h->N * h->N);
+  const dim3 grid(nn, (nn + 255) / 256);
+  if (grid.y > 65535) return fail(RCHEM_ERR_TOO_LARGE, "dense tensor: N too large for the fill grid");
+  tensor_fill_kernel<<<grid, 256, 0, h->stream>>>(I_dev, h->N, (int)h->shells.shells.size(),
+                                                  h->d_fn_shell, h->d_pair_key, h->d_pair_fwd);
+  CUDA_OK(cudaGetLastError());
+  h->stats.launches += 1;
+  return RCHEM_OK;
 }
 
 int rchem_jk_inmem_device(int n, const double* I_dev, const double* D_dev, double* JK_dev,

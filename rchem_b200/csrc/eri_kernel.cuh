@@ -215,15 +215,9 @@ __global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
       for (int o = 0; o < C::kOut; ++o) {
         const int d = o % ND, c = (o / ND) % NC, b = (o / (ND * NC)) % NB, a = o / (ND * NC * NB);
         const size_t i = bfA + a, j = bfB + b, k = bfC + c, l = bfD + d;
-        const double v = out[o];
-        I[((i * N + j) * N + k) * N + l] = v;
-        I[((j * N + i) * N + k) * N + l] = v;
-        I[((i * N + j) * N + l) * N + k] = v;
-        I[((j * N + i) * N + l) * N + k] = v;
-        I[((k * N + l) * N + i) * N + j] = v;
-        I[((l * N + k) * N + i) * N + j] = v;
-        I[((k * N + l) * N + j) * N + i] = v;
-        I[((l * N + k) * N + j) * N + i] = v;
+        // only the canonical element (stored pair orientations, bra pair >= ket pair); the other
+        // seven permutations are filled in by tensor_fill_kernel (engine.cu)
+        I[((i * N + j) * N + k) * N + l] = out[o];
       }
     }
     return;
