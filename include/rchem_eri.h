@@ -109,6 +109,15 @@ int rchem_jk_direct_device(rchem_basis* b, const double* D_dev, double* JK_dev, 
 int rchem_jk_inmem_device(int n, const double* I_dev, const double* D_dev, double* JK_dev,
                           void* cuda_stream);
 
+/* ---------------- one-electron matrices: the step before the hot path ------------------
+ * basis::S(&basis), basis::T(&basis), basis::V(&basis, &atomcoords, &atomnos)
+ * (basis.rs:234-338): N x N, symmetric, host buffers.  Evaluated on the GPU with the exact
+ * Boys function, like the reference's os86 path (os86.rs:629, 672, 722). */
+int rchem_overlap(rchem_basis* b, double* S_host);
+int rchem_kinetic(rchem_basis* b, double* T_host);
+int rchem_nuclear(rchem_basis* b, int natoms, const double* atomcoords, const uint64_t* atomnos,
+                  double* V_host);
+
 /* ---------------- screening --------------------------------------------------------- */
 /* Shell pairs in kernel order (batch by batch, Schwarz-descending inside a batch).
  * Returns the number of pairs; arrays may be NULL to query the count.

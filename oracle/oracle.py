@@ -72,6 +72,13 @@ def lib():
         L.orc_eval_quartets.argtypes = basis_args + [_ip, C.c_int64, C.c_void_p, C.c_int]
         L.orc_set_reference_kernel.restype = None
         L.orc_set_reference_kernel.argtypes = [C.c_void_p]
+        L.orc_one_electron.restype = None
+        L.orc_one_electron.argtypes = basis_args + [C.c_int, C.c_int, _dp, _dp, _dp]
+        for f in (L.orc_overlap, L.orc_kinetic):
+            f.restype = C.c_double
+            f.argtypes = [C.c_double, C.c_double, _dp, _dp, _ip]
+        L.orc_nuclear.restype = C.c_double
+        L.orc_nuclear.argtypes = [C.c_double, C.c_double, _dp, _dp, _dp, _ip]
         L.orc_quartet_list.restype = C.c_int64
         L.orc_quartet_list.argtypes = [_dp, C.c_int, _dp, C.c_int, C.c_int, C.c_double,
                                        C.c_void_p, C.c_int64]
@@ -218,6 +225,16 @@ def jk_inmem(I, D):
                        np.ascontiguousarray(D, dtype=np.float64).reshape(-1), J.reshape(-1),
                        K.reshape(-1))
     return J, K
+
+
+def one_electron(basis, which, atomnos=None, coords=None):
+    """basis::S / T / V (basis.rs:234-338) with exact Boys (os86 path): which = 'S', 'T', 'V'"""
+    M = np.zeros((basis.n, basis.n))
+    z = np.ascontiguousarray(atomnos if atomnos is not None else [0], dtype=np.float64)
+    xyz = np.ascontiguousarray(coords if coords is not None else [[0, 0, 0]], dtype=np.float64).reshape(-1)
+    lib().orc_one_electron(*basis.args(), "STV".index(which), len(z) if which == "V" else 0, xyz, z,
+                           M.reshape(-1))
+    return M
 
 
 def contracted_eri(basis, mu, nu, la, si, boys=BOYS_REFERENCE):

@@ -4,6 +4,7 @@ Host-side mirror of the reference's public interface for this path (src/basis.rs
 over the C ABI of ``librchem_b200.so`` (include/rchem_eri.h) with ctypes:
 
     Basis.new(atomnos, coords, name)      <- basis::Basis::new        basis.rs:182-211
+    S(basis), T(basis), V(basis, xyz, Z)  <- basis::S / T / V         basis.rs:234-338
     build_I(basis)                        <- basis::build_I           basis.rs:430-460
     JK_direct(J, K, basis, D)             <- basis::JK_direct         basis.rs:383-428
     JK_inmem(I, D)                        <- basis::JK_inmem          basis.rs:462-484
@@ -86,6 +87,9 @@ _sig("rchem_jk_inmem", C.c_int, [C.c_int, _dp, _dp, _dp, _dp])
 _sig("rchem_build_I_device", C.c_int, [_vp, _vp])
 _sig("rchem_jk_direct_device", C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int])
 _sig("rchem_jk_inmem_device", C.c_int, [C.c_int, _vp, _vp, _vp, _vp])
+_sig("rchem_overlap", C.c_int, [_vp, _dp])
+_sig("rchem_kinetic", C.c_int, [_vp, _dp])
+_sig("rchem_nuclear", C.c_int, [_vp, C.c_int, _dp, C.POINTER(C.c_uint64), _dp])
 _sig("rchem_schwarz", C.c_int64, [_vp, _vp, _vp, _vp, _vp])
 _sig("rchem_quartet_list", C.c_int64, [_vp, _vp, C.c_int64])
 _sig("rchem_get_stats", C.c_int, [_vp, C.POINTER(Stats)])
@@ -236,6 +240,30 @@ class Basis:
 
     def build_I_device(self, I_ptr):
         _check(_lib.rchem_build_I_device(self._h, _vp(I_ptr)))
+
+
+def S(basis_set):
+    """basis::S(&basis_set): overlap matrix (basis.rs:234-251)."""
+    out = np.zeros((basis_set.nbf, basis_set.nbf))
+    _check(_lib.rchem_overlap(basis_set._h, out.reshape(-1)))
+    return out
+
+
+def T(basis_set):
+    """basis::T(&basis_set): kinetic-energy matrix (basis.rs:273-290)."""
+    out = np.zeros((basis_set.nbf, basis_set.nbf))
+    _check(_lib.rchem_kinetic(basis_set._h, out.reshape(-1)))
+    return out
+
+
+def V(basis_set, atomcoords, atomnos):
+    """basis::V(&basis_set, &atomcoords, &atomnos): nuclear-attraction matrix (basis.rs:316-338)."""
+    xyz = np.ascontiguousarray(atomcoords, dtype=np.float64).reshape(-1, 3)
+    z = np.ascontiguousarray(atomnos, dtype=np.uint64)
+    out = np.zeros((basis_set.nbf, basis_set.nbf))
+    _check(_lib.rchem_nuclear(basis_set._h, len(z), xyz.reshape(-1),
+                              z.ctypes.data_as(C.POINTER(C.c_uint64)), out.reshape(-1)))
+    return out
 
 
 def build_I(basis_set):

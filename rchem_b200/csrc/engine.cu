@@ -40,6 +40,10 @@ static int fail(int code, const std::string& msg) {
   return code;
 }
 int fail_public(int code, const std::string& msg) { return fail(code, msg); }
+// one_electron.cu
+int one_electron_host(int n, const double* origins, const int* powers, const int* prim_offset,
+                      const double* exps, const double* coefs, const double* norms, int which,
+                      int natoms, const double* atomcoords, const double* charges, double* M);
 #define CUDA_OK(expr)                                                                      \
   do {                                                                                     \
     cudaError_t e_ = (expr);                                                               \
@@ -967,6 +971,30 @@ int rchem_jk_inmem(int n, const double* I, const double* D, double* J, double* K
   cudaFree(dI); cudaFree(dD); cudaFree(dJK);
   if (e != cudaSuccess) return fail(RCHEM_ERR_CUDA, cudaGetErrorString(e));
   return rc;
+}
+
+// ---------------- one-electron matrices -------------------------------------
+static int one_electron(rchem_basis* h, int which, int natoms, const double* atomcoords,
+                        const uint64_t* atomnos, double* M) {
+  if (!h || !M) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
+  if (which == 2 && (natoms <= 0 || !atomcoords || !atomnos))
+    return fail(RCHEM_ERR_INVALID_ARG, "V needs the atom list");
+  const int n = h->N;
+  std::vector<double> origins(3 * (size_t)n), exps(h->nprim), coefs(h->nprim), norms(h->nprim), Z;
+  std::vector<int> powers(3 * (size_t)n), off(n + 1);
+  int rc = rchem_basis_export(h, origins.data(), powers.data(), off.data(), exps.data(),
+                              coefs.data(), norms.data());
+  if (rc) return rc;
+  for (int c = 0; c < natoms && which == 2; ++c) Z.push_back((double)atomnos[c]);
+  return one_electron_host(n, origins.data(), powers.data(), off.data(), exps.data(), coefs.data(),
+                           norms.data(), which, natoms, atomcoords, Z.data(), M);
+}
+
+int rchem_overlap(rchem_basis* h, double* S) { return one_electron(h, 0, 0, nullptr, nullptr, S); }
+int rchem_kinetic(rchem_basis* h, double* T) { return one_electron(h, 1, 0, nullptr, nullptr, T); }
+int rchem_nuclear(rchem_basis* h, int natoms, const double* atomcoords, const uint64_t* atomnos,
+                  double* V) {
+  return one_electron(h, 2, natoms, atomcoords, atomnos, V);
 }
 
 // ---------------- screening ---------------------------------------------------------------

@@ -14,34 +14,11 @@
 
 #include "../../include/rchem_eri.h"
 #include "eri_core.h"
+#include "tho_device.cuh"
 
 namespace rchem {
 
 constexpr int kMaxAxis = 12;  // 12! is the last factorial the reference's int fact() can hold
-
-__device__ __forceinline__ double dfact(int n) {
-  double r = 1.0;
-  for (int k = 2; k <= n; ++k) r *= k;
-  return r;
-}
-__device__ __forceinline__ double ipow(double x, int n) {  // n >= 0
-  double r = 1.0;
-  for (int k = 0; k < n; ++k) r *= x;
-  return r;
-}
-__device__ __forceinline__ double binom(int a, int b) { return dfact(a) / (dfact(b) * dfact(a - b)); }
-__device__ __forceinline__ double fact_ratio2(int a, int b) {
-  return dfact(a) / dfact(b) / dfact(a - 2 * b);
-}
-
-// sum_t C(ia,s-t) C(ib,t) xpa^(ia-s+t) xpb^(ib-t)            (cints.c:291-298)
-__device__ double binomial_prefactor(int s, int ia, int ib, double xpa, double xpb) {
-  double sum = 0.0;
-  for (int t = 0; t <= s; ++t)
-    if (s - ia <= t && t <= ib)
-      sum += binom(ia, s - t) * binom(ib, t) * ipow(xpa, ia - s + t) * ipow(xpb, ib - t);
-  return sum;
-}
 
 // fB (cints.c:33-40); (4g)^(r-i) has a non-positive exponent
 __device__ double f_b(int i, int l1, int l2, double p, double a, double b, int r, double g) {
@@ -64,22 +41,6 @@ __device__ void b_axis(double* B, int l1, int l2, int l3, int l4, double p, doub
             B[top - u] += fb * ((u & 1) ? -1.0 : 1.0) * fact_ratio2(top, u) *
                           ipow(q - p, top - 2 * u) / ipow(delta, top - u);
         }
-}
-
-// F_m(x), converged (used for boys = exact): positive series below 36, asymptotic above
-__device__ double boys_converged(int m, double x) {
-  if (x < 36.0) {
-    double term = 1.0 / (2 * m + 1), sum = term;
-    for (int k = 1; k < 400; ++k) {
-      term *= 2.0 * x / (2 * m + 2 * k + 1);
-      sum += term;
-      if (term < 1e-17 * sum) break;
-    }
-    return exp(-x) * sum;
-  }
-  double f = 0.88622692545275801365 * rsqrt(x);
-  for (int k = 0; k < m; ++k) f *= (2 * k + 1) / (2.0 * x);
-  return f;
 }
 
 __global__ void prim_batch_kernel(long long n, const double* __restrict__ centres,

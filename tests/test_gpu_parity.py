@@ -343,3 +343,31 @@ def test_rhf_water_crawford_energy(rc, orc, geo):
     assert it < 100
     assert abs(e_new - (-82.944446488)) < 5e-8
     assert abs(e_new - (-82.944446990)) < 1e-6  # Crawford's published value
+
+
+# ---- widened rows: one-electron matrices and the RHF driver --------------------
+@pytest.mark.parametrize("basis_name", ["STO-3G", "6-31G*"])
+def test_one_electron_matrices_vs_oracle(rc, orc, geo, basis_name):
+    z, x = geo.water_cluster(2)
+    b = rc.Basis.new(z, x, basis_name)
+    ob = orc.make_basis(z, x, basis_name)
+    for name, got in (("S", rc.S(b)), ("T", rc.T(b)), ("V", rc.V(b, x, z))):
+        ref = orc.one_electron(ob, name, z, x)
+        assert np.abs(got - ref).max() < 1e-12, name
+        assert np.array_equal(got, got.T)
+
+
+def test_rhf_driver_on_device_integrals(rc, geo):
+    """rchem.rs main(): S, T, V and J/K all from the GPU library.  With the exact-Boys
+    one-electron integrals of the reference's os86 path and libpyquante2-flavoured J/K the
+    converged energy sits within 1e-6 of Crawford's published -82.944446990."""
+    from rchem_b200 import scf
+
+    z, x = geo.molecule(geo.WATER_CRAWFORD)
+    b = rc.Basis.new(z, x, "STO-3G")
+    e, its, C, D = scf.rhf(b, z, x)
+    assert its < 60
+    assert abs(e - (-82.944446990)) < 1e-6
+    b.set_boys(rc.BOYS_EXACT)
+    e2, _, _, _ = scf.rhf(b, z, x)
+    assert abs(e2 - e) < 1e-6 and abs(e2 - (-82.944446990)) < 1e-6

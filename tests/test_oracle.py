@@ -150,3 +150,32 @@ def test_quartet_list_builder(orc):
     assert [tuple(r) for r in out.tolist()] == expect
     out = orc.quartet_list(Qb, Qb[:3], False, 0.0)
     assert len(out) == 15
+
+
+# ---- one-electron integrals (the step before the hot path; exact-Boys os86 semantics) ----------
+def test_one_electron_golden_os86(orc):
+    # os86.rs:939-1004: get_overlap / get_kinetic / get_nuclear known answers
+    L = orc.lib()
+    ra, rb, rc = np.zeros(3), np.array([0.5, 0.8, -0.2]), np.array([0.5, 0.8, 0.2])
+    pw = lambda *a: np.array(a, dtype=np.int32)
+    for p, v in (((0, 0, 0, 0, 0, 0), 0.20373275913014607), ((1, 0, 0, 0, 0, 0), 0.062005622343957505),
+                 ((1, 1, 0, 1, 1, 0), -0.00043801221837779696), ((2, 1, 0, 1, 1, 0), -0.0002385994651113168)):
+        assert abs(L.orc_overlap(1.8, 2.8, ra, rb, pw(*p)) - v) < 1e-16
+    for p, v in (((0, 0, 0, 0, 0, 0), 0.3652714583525358), ((1, 0, 0, 0, 0, 0), 0.2514265587836556),
+                 ((2, 2, 2, 2, 2, 2), -7.40057384314e-05)):
+        assert abs(L.orc_kinetic(1.8, 2.0, ra, rb, pw(*p)) - v) < (3e-16 if abs(v) > 1e-3 else 1e-16)
+    for p, v in (((0, 0, 0, 0, 0, 0), -0.49742209545104593), ((1, 0, 0, 0, 0, 0), -0.15987439458254471),
+                 ((2, 2, 2, 0, 0, 0), -0.003801373531942607), ((1, 1, 1, 1, 1, 1), 8.8415484347060993e-5)):
+        assert abs(L.orc_nuclear(1.8, 2.0, ra, rb, rc, pw(*p)) - v) < 1e-15
+
+
+def test_one_electron_matrices_water(orc, geo):
+    z, x = geo.molecule(geo.WATER_CRAWFORD)
+    b = orc.make_basis(z, x, "STO-3G")
+    S = orc.one_electron(b, "S")
+    # contraction coefficients are not renormalised: diag(S) = 1 +- 3e-8 (SURVEY 8a note)
+    assert np.abs(np.diag(S) - 1).max() < 1e-7 and np.abs(S - S.T).max() == 0
+    T, V = orc.one_electron(b, "T"), orc.one_electron(b, "V", z, x)
+    # Crawford's published core Hamiltonian elements for this geometry/basis
+    H = T + V
+    assert abs(H[0, 0] - (-32.5773954)) < 2e-6 and abs(H[1, 0] - (-7.5788328)) < 2e-6
