@@ -26,7 +26,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librchem_b200.so")
 
 BOYS_REFERENCE, BOYS_EXACT = 0, 1
-OPT_BOYS, OPT_SCHWARZ_TAU, OPT_DEVICE = 1, 2, 3
+OPT_BOYS, OPT_SCHWARZ_TAU, OPT_DEVICE, OPT_PRIM_EPS = 1, 2, 3, 4
 
 
 class RchemError(RuntimeError):
@@ -199,6 +199,10 @@ class Basis:
 
     def set_schwarz_tau(self, tau):
         _check(_lib.rchem_set_option(self._h, OPT_SCHWARZ_TAU, float(tau)))
+
+    def set_prim_eps(self, eps):
+        """Primitive-pair prefactor cutoff (default 1e-20; 0 keeps every primitive pair)."""
+        _check(_lib.rchem_set_option(self._h, OPT_PRIM_EPS, float(eps)))
 
     def set_device(self, ordinal):
         _check(_lib.rchem_set_option(self._h, OPT_DEVICE, float(ordinal)))

@@ -234,6 +234,7 @@ struct rchem_basis {
   // options
   int boys = kBoysReference;
   double tau = 0.0;
+  double prim_eps = kPrimPairEps;
   int device = 0;
   // device state
   bool ready = false;
@@ -279,7 +280,7 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
     shA[s] = bt.shA[src];
     shB[s] = bt.shB[src];
     if (!bt.Q.empty()) Q[s] = bt.Q[src];
-    build_prim_pairs(A, B, &pps);
+    build_significant_prim_pairs(A, B, h->prim_eps, &pps);  // pps.size() == bt.K2 by construction
     for (int k = 0; k < bt.K2; ++k) {
       const PrimPair& pp = pps[k];
       const double f[6] = {pp.zeta, pp.rzeta, pp.Px, pp.Py, pp.Pz, pp.pref};
@@ -370,11 +371,13 @@ int ensure_ready(rchem_basis* h) {
   // shell pairs -> batches keyed by (la, lb, K2); batch order = pair class, then K2 descending
   const auto& sh = h->shells.shells;
   std::map<std::tuple<int, int, int>, Batch> by_key;
+  std::vector<PrimPair> scratch_pps;
   for (int i = 0; i < (int)sh.size(); ++i)
     for (int j = 0; j <= i; ++j) {
       int a = i, b = j;
       if (sh[a].l < sh[b].l) std::swap(a, b);
-      const int K2 = (int)(sh[a].exps.size() * sh[b].exps.size());
+      // K2 = number of SIGNIFICANT primitive pairs (pair_build.h kPrimPairEps)
+      const int K2 = build_significant_prim_pairs(sh[a], sh[b], h->prim_eps, &scratch_pps);
       const int cls = sh[a].l * (sh[a].l + 1) / 2 + sh[b].l;
       Batch& bt = by_key[std::make_tuple(cls, -K2, 0)];
       bt.la = sh[a].l; bt.lb = sh[b].l; bt.K2 = K2;
@@ -793,6 +796,11 @@ int rchem_set_option(rchem_basis* h, int key, double value) {
       if (h->ready) return fail(RCHEM_ERR_INVALID_ARG, "device is fixed after the first compute call");
       h->device = (int)value;
       return RCHEM_OK;
+    case RCHEM_OPT_PRIM_EPS:
+      if (h->ready) return fail(RCHEM_ERR_INVALID_ARG, "prim_eps is fixed after the first compute call");
+      if (!(value >= 0.0)) return fail(RCHEM_ERR_INVALID_ARG, "prim_eps must be >= 0");
+      h->prim_eps = value;
+      return RCHEM_OK;
   }
   return fail(RCHEM_ERR_INVALID_ARG, "unknown option");
 }
@@ -803,6 +811,7 @@ double rchem_get_option(const rchem_basis* h, int key) {
     case RCHEM_OPT_BOYS: return h->boys;
     case RCHEM_OPT_SCHWARZ_TAU: return h->tau;
     case RCHEM_OPT_DEVICE: return h->device;
+    case RCHEM_OPT_PRIM_EPS: return h->prim_eps;
   }
   return std::numeric_limits<double>::quiet_NaN();
 }

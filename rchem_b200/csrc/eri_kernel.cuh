@@ -320,10 +320,10 @@ __global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
 #endif
 template <int LA, int LB, int LC, int LD> struct BlockCfg {
   // small classes: RCHEM_BLK_T_SMALL threads, 2 blocks per SM (<= 64 registers); medium ones
-  // (<= 31 targets): 256 threads, 2 blocks per SM (<= 128 registers); large ones: 256 threads
+  // (<= 18 targets): 256 threads, 2 blocks per SM (<= 128 registers); large ones: 256 threads
   static constexpr int kTargets = EriClass<LA, LB, LC, LD>::kTargets;
   static constexpr bool kSmall = kTargets <= 9;
-  static constexpr bool kMedium = !kSmall && kTargets <= 31;
+  static constexpr bool kMedium = !kSmall && kTargets <= 18;
   static constexpr int kThreadsBlk = kSmall ? RCHEM_BLK_T_SMALL : 256;
   static constexpr int kMinBlocks = kSmall ? RCHEM_BLK_MINB_SMALL : (kMedium ? 2 : 1);
   static constexpr int kKetsPerBlock = kThreadsBlk * 8;

@@ -5,6 +5,7 @@
 // (cints.c:391-394), 1./gamma by an IEEE division.  This file must be compiled without
 // FMA contraction (-ffp-contract=off), like the reference's x86-64 build.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -13,6 +14,12 @@
 #include "eri_core.h"
 
 namespace rchem {
+
+// Primitive pairs whose prefactor (contraction coefficients x norms x Gaussian-product
+// exponential / zeta) is below this are dropped: each contributes < ~1e-15 to any integral,
+// three orders below the 1e-12 parity tolerance.  Tight core primitives on different atoms
+// are the typical case (exp(-alpha beta R^2 / zeta) underflows).
+constexpr double kPrimPairEps = 1e-20;
 
 // Primitive pairs of (A,B), A-primitive major: k = i*nprim(B) + j.
 inline void build_prim_pairs(const Shell& A, const Shell& B, std::vector<PrimPair>* out) {
@@ -33,6 +40,20 @@ inline void build_prim_pairs(const Shell& A, const Shell& B, std::vector<PrimPai
       pp.pref = A.cn[i] * B.cn[j] * std::exp(-aa * ab * rab2 / pp.zeta) / pp.zeta;
       out->push_back(pp);
     }
+}
+
+// The significant primitive pairs of (A,B): sorted by |pref| descending, truncated after the
+// last one with |pref| >= eps (at least one is kept).  Returns the count.
+inline int build_significant_prim_pairs(const Shell& A, const Shell& B, double eps,
+                                        std::vector<PrimPair>* out) {
+  build_prim_pairs(A, B, out);
+  std::stable_sort(out->begin(), out->end(), [](const PrimPair& x, const PrimPair& y) {
+    return std::fabs(x.pref) > std::fabs(y.pref);
+  });
+  size_t n = out->size();
+  while (n > 1 && !(std::fabs((*out)[n - 1].pref) >= eps)) --n;
+  out->resize(n);
+  return (int)n;
 }
 
 // exact Boys tables for boys_exact (eri_core.h): one table per total angular momentum
