@@ -502,7 +502,7 @@ int ensure_tasks(rchem_basis* h) {
       EriBlockInfo info{0, 0};
       find_block_launcher(B.la, B.lb, K.la, K.lb, &info);
       tt.smem_bytes = (size_t)2 * (ncart(B.la) + ncart(B.lb)) * h->N * sizeof(double) +
-                      (size_t)B.K2 * sizeof(PrimPair);
+                      (size_t)B.K2 * sizeof(PrimPair) + (size_t)info.kets_per_block * sizeof(int) + 64;
       const bool rows_fit = tt.smem_bytes <= kMaxBlockSmem && info.threads > 0;
       // a bra pair is "heavy" when its ket prefix fills the block kernel's threads at least
       // kHeavyPasses times (the last, partial pass of a block idles most of its warps)

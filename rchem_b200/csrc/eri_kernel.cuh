@@ -114,8 +114,12 @@ __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const B
   const int sk = t.ket.stride;
   const double Cx = __ldg(gk), Cy = __ldg(gk + sk), Cz = __ldg(gk + 2 * sk);
 
+  // Small classes keep the contraction accumulators in registers (fully unrolled init ->
+  // scalar replacement).  Past ~100 targets they cannot fit; a rolled init loop indexes the
+  // array dynamically, which pins it in (L1-cached) local memory from the start instead of
+  // sending ptxas into its spill-everything fallback.
   double acc[C::kTargets];
-#pragma unroll
+#pragma unroll(C::kTargets <= 100 ? C::kTargets : 1)
   for (int i = 0; i < C::kTargets; ++i) acc[i] = 0.0;
 
   const int K2b = t.bra.K2, K2k = t.ket.K2;
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
 // the accumulators K[a,:], K[b,:] (a in A, b in B) live in SHARED memory, so the four
 // mixed-index K updates and their density factors never touch L1/L2 with scattered 8-byte
 // accesses; the bra block of J accumulates in registers over the whole ket range.
-// Dynamic shared memory: 2*(NA+NB)*N doubles + K2_bra primitive pairs.
+// Dynamic shared memory: 2*(NA+NB)*N doubles + K2_bra primitive pairs + the ket index list.
 // ---------------------------------------------------------------------------------------
 #ifndef RCHEM_BLK_T_SMALL
 #define RCHEM_BLK_T_SMALL 512
@@ -331,6 +335,11 @@ template <int LA, int LB, int LC, int LD> struct BlockCfg {
 
 __device__ __forceinline__ void smem_add(double* addr, double v) { atomicAdd(addr, v); }
 
+// Boys argument of the leading primitive pairs from which a quartet is scheduled with the
+// far-field group (kBoysXMax plus a margin for the tighter primitives)
+constexpr double kFarSplitX = 56.0;
+constexpr int kPartitionMinPrims = 16;
+
 template <int LA, int LB, int LC, int LD, int BOYS>
 __global__ void __launch_bounds__(BlockCfg<LA, LB, LC, LD>::kThreadsBlk,
                                   BlockCfg<LA, LB, LC, LD>::kMinBlocks)
@@ -341,6 +350,7 @@ eri_jk_block_kernel(const EriTask t) {
   constexpr int T = BlockCfg<LA, LB, LC, LD>::kThreadsBlk;
   extern __shared__ double smem[];
   __shared__ int s_info[3];
+  __shared__ int s_cnt[3];
 
   const long long blk = (long long)blockIdx.x * t.nranks + t.rank;
   if (blk >= t.nblocks_heavy) return;
@@ -389,9 +399,71 @@ eri_jk_block_kernel(const EriTask t) {
     Dab[i] = __ldg(t.bra.Dp + (size_t)i * sb + p);
     jab[i] = 0.0;
   }
+  // Scheduling of this block's kets (reference Boys flavour only).  Lanes of a warp see
+  // unrelated Boys arguments, and the three regimes cost very differently: far field
+  // (x >= 48: a reciprocal square root), grid (Taylor expansion), and grid + truncation
+  // correction (x below ref_exact_from(L), a few % of the quartets).  Left in list order,
+  // almost every warp contains one lane of the expensive regime and pays for it with 31 idle
+  // lanes.  The kets are therefore reordered in shared memory into [far | grid | corrected],
+  // classified by the Boys argument of the most diffuse primitive pairs (stored first), so
+  // that warps work on one regime.  Misclassified primitives are still evaluated correctly;
+  // the split only decides which lanes run together.  With the exact flavour the reordering
+  // was measured to cost more (scattered ket reads) than it saves, so it is skipped.
+  int* s_list = reinterpret_cast<int*>(s_bra + t.bra.K2);  // [q1 - q0]
+  const int nk = q1 - q0;
+  // ... and it only pays when a quartet carries enough primitive work to amortise the two
+  // classification passes and the scattered ket reads (measured: deep contractions gain
+  // 10 %, single-primitive quartets lose 2 %).
+  const bool kPartition = BOYS == kBoysReference && t.bra.K2 * t.ket.K2 >= kPartitionMinPrims;
+  if (kPartition) {
+    if (tid < 3) s_cnt[tid] = 0;
+    __syncthreads();
+    const PrimPair b0 = s_bra[0];
+    const size_t fs = (size_t)t.ket.K2 * sk;
+    const double xcorr = ref_exact_from(C::kL) + 2.0;
+    unsigned cls_bits = 0;  // 2 bits per pass: 0 far, 1 grid, 2 corrected
+    int pass = 0;
+    for (int base = 0; base < nk; base += T, ++pass) {
+      const int i = base + tid;
+      int cls = 3;  // invalid
+      if (i < nk) {
+        const double* kp = t.ket.prim + (q0 + i);  // primitive pair 0 (most diffuse) of ket q0+i
+        const double eta = __ldg(kp);
+        const double dx = b0.Px - __ldg(kp + 2 * fs), dy = b0.Py - __ldg(kp + 3 * fs),
+                     dz = b0.Pz - __ldg(kp + 4 * fs);
+        const double x0 = b0.zeta * eta / (b0.zeta + eta) * (dx * dx + dy * dy + dz * dz);
+        cls = x0 >= kFarSplitX ? 0 : (x0 >= xcorr ? 1 : 2);
+      }
+      cls_bits |= (unsigned)cls << (2 * pass);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+        if (lane == 0 && m) atomicAdd(&s_cnt[c], __popc(m));
+      }
+    }
+    __syncthreads();
+    const int n_far = s_cnt[0], n_grid = s_cnt[1];
+    __syncthreads();
+    if (tid < 3) s_cnt[tid] = tid == 0 ? 0 : (tid == 1 ? n_far : n_far + n_grid);  // write cursors
+    __syncthreads();
+    pass = 0;
+    for (int base = 0; base < nk; base += T, ++pass) {
+      const int i = base + tid;
+      const int cls = (cls_bits >> (2 * pass)) & 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+        int at = 0;
+        if (lane == 0 && m) at = atomicAdd(&s_cnt[c], __popc(m));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (cls == c) s_list[at + __popc(m & ((1u << lane) - 1u))] = q0 + i;
+      }
+    }
+  }
   __syncthreads();
 
-  for (int q = q0 + tid; q < q1; q += T) {
+  for (int it = tid; it < nk; it += T) {
+    const int q = kPartition ? s_list[it] : q0 + it;
     double out[C::kOut];
     int bfC, bfD;
     const double scale =

@@ -42,8 +42,8 @@ inline void build_prim_pairs(const Shell& A, const Shell& B, std::vector<PrimPai
     }
 }
 
-// The significant primitive pairs of (A,B): sorted by |pref| descending, truncated after the
-// last one with |pref| >= eps (at least one is kept).  Returns the count.
+// The significant primitive pairs of (A,B): those with |pref| >= eps (at least one is kept),
+// ordered by increasing zeta.  Returns the count.
 inline int build_significant_prim_pairs(const Shell& A, const Shell& B, double eps,
                                         std::vector<PrimPair>* out) {
   build_prim_pairs(A, B, out);
@@ -53,6 +53,10 @@ inline int build_significant_prim_pairs(const Shell& A, const Shell& B, double e
   size_t n = out->size();
   while (n > 1 && !(std::fabs((*out)[n - 1].pref) >= eps)) --n;
   out->resize(n);
+  // most diffuse pair first: its Boys argument is (nearly) the smallest of the shell pair,
+  // which is what the kernels' near/far scheduling looks at
+  std::stable_sort(out->begin(), out->end(),
+                   [](const PrimPair& x, const PrimPair& y) { return x.zeta < y.zeta; });
   return (int)n;
 }
 
