@@ -371,3 +371,85 @@ def test_rhf_driver_on_device_integrals(rc, geo):
     b.set_boys(rc.BOYS_EXACT)
     e2, _, _, _ = scf.rhf(b, z, x)
     assert abs(e2 - e) < 1e-6 and abs(e2 - (-82.944446990)) < 1e-6
+
+
+# ---- edge cases: tiny, ragged and degenerate inputs ---------------------------------------------------
+def test_single_function_and_single_shell(rc, orc):
+    # one H atom, STO-3G: one s function, one shell, one pair, one quartet
+    z, x = np.array([1], dtype=np.uint64), np.zeros((1, 3))
+    b = rc.Basis.new(z, x, "STO-3G")
+    ob = orc.make_basis(z, x, "STO-3G")
+    I = rc.build_I(b)
+    assert I.shape == (1, 1, 1, 1) and abs(I[0, 0, 0, 0] - orc.contracted_eri(ob, 0, 0, 0, 0)) < TOL
+    J, K = np.zeros((1, 1)), np.zeros((1, 1))
+    rc.JK_direct(J, K, b, np.array([[0.7]]))
+    assert abs(J[0, 0] - 0.7 * I[0, 0, 0, 0]) < TOL and abs(K[0, 0] - 0.7 * I[0, 0, 0, 0]) < TOL
+    # one O atom, 6-31G*: every shell on one centre (all Boys arguments are 0 -> the 1e-8 clamp)
+    z, x = np.array([8], dtype=np.uint64), np.array([[0.3, -0.2, 0.1]])
+    b = rc.Basis.new(z, x, "6-31G*")
+    ob = orc.make_basis(z, x, "6-31G*")
+    I = rc.build_I(b)
+    q = np.random.default_rng(9).integers(0, ob.n, size=(1500, 4)).astype(np.int32)
+    assert np.abs(I[q[:, 0], q[:, 1], q[:, 2], q[:, 3]] - orc.eval_quartets(ob, q)).max() < TOL
+
+
+def test_ragged_custom_basis(rc, orc):
+    """Shells with ragged contraction lengths (1..5 primitives), random exponents, coefficients
+    of both signs and s/p/d mixed on four centres, passed as explicit CGTOs."""
+    rng = np.random.default_rng(123)
+    centres = rng.uniform(-1.8, 1.8, size=(4, 3))
+    origins, powers, off, exps, coefs, norms = [], [], [0], [], [], []
+    L = orc.lib()
+    for c, (l, k) in zip([0, 0, 1, 1, 2, 3, 3, 2], [(0, 5), (1, 2), (0, 1), (2, 1), (1, 3), (0, 4), (2, 2), (0, 2)]):
+        e = np.exp(rng.uniform(np.log(0.2), np.log(30.0), size=k))
+        cf = rng.uniform(-1.0, 1.0, size=k)
+        for pw in orc.ijk_list(l):
+            origins.append(centres[c]); powers.append(pw)
+            for ee, cc in zip(e, cf):
+                exps.append(ee); coefs.append(cc)
+                norms.append(L.orc_normalization(np.ascontiguousarray(pw), ee))
+            off.append(len(exps))
+    ob = orc.FlatBasis(origins, powers, off, exps, coefs, norms)
+    b = rc.Basis.from_cgtos(ob.origins, ob.powers, ob.prim_offset, ob.exps, ob.coefs, ob.norms)
+    n = ob.n
+    assert n == 1 + 3 + 1 + 6 + 3 + 1 + 6 + 1
+    I = rc.build_I(b)
+    I_ref = orc.build_I(ob)
+    assert np.abs(I - I_ref).max() < TOL * max(1.0, np.abs(I_ref).max())
+    D = np.random.default_rng(5).standard_normal((n, n)); D = (D + D.T) / 2
+    J, K = np.zeros((n, n)), np.zeros((n, n))
+    rc.JK_direct(J, K, b, D)
+    Jo, Ko = orc.jk_inmem(I_ref, D)
+    scale = max(1.0, np.abs(Jo).max(), np.abs(Ko).max())
+    assert np.abs(J - Jo).max() < TOL * scale and np.abs(K - Ko).max() < TOL * scale
+
+
+def test_everything_screened_and_zero_density(rc, geo):
+    z, x = geo.water_cluster(2)
+    b = rc.Basis.new(z, x, "STO-3G")
+    n = b.nbf
+    D = geo.synthetic_density(n)
+    b.set_schwarz_tau(1e30)  # nothing survives
+    J, K = np.ones((n, n)), np.ones((n, n))
+    rc.JK_direct(J, K, b, D)
+    assert not J.any() and not K.any() and b.stats()["shell_quartets"] == 0
+    assert not rc.build_I(b).any()
+    b.set_schwarz_tau(0.0)
+    rc.JK_direct(J, K, b, np.zeros((n, n)))
+    assert not J.any() and not K.any()
+
+
+def test_prim_eps_option_does_not_change_results(rc, orc, geo):
+    z, x = geo.water_cluster(3)
+    n = None
+    out = []
+    for eps in (1e-20, 0.0):
+        b = rc.Basis.new(z, x, "6-31G")
+        b.set_prim_eps(eps)
+        n = b.nbf
+        D = geo.synthetic_density(n)
+        J, K = np.zeros((n, n)), np.zeros((n, n))
+        rc.JK_direct(J, K, b, D)
+        out.append((J, K, b.stats()["prim_quartets"]))
+    assert out[0][2] < out[1][2]  # primitive pairs were dropped ...
+    assert np.abs(out[0][0] - out[1][0]).max() < 1e-13 and np.abs(out[0][1] - out[1][1]).max() < 1e-13
