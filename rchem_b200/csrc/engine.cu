@@ -255,7 +255,8 @@ struct rchem_basis {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // The tasks of one J/K (or tensor) build are independent kernels; they are spread over a
   // few auxiliary streams so the tail of one launch overlaps the head of the next.
-  static constexpr int kAuxStreams = 6;
+  static constexpr int kAuxStreams = 16;  // upper bound; RCHEM_STREAMS (default 12) are used
+  int n_aux = 12;
   cudaStream_t aux[kAuxStreams] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kAuxStreams] = {};
   rchem_stats stats{};
@@ -349,6 +350,8 @@ int ensure_ready(rchem_basis* h) {
   CUDA_OK(cudaEventCreate(&h->ev0));
   CUDA_OK(cudaEventCreate(&h->ev1));
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  if (const char* e = std::getenv("RCHEM_STREAMS"))
+    h->n_aux = std::min((int)rchem_basis::kAuxStreams, std::max(1, atoi(e)));
   for (int i = 0; i < rchem_basis::kAuxStreams; ++i) {
     CUDA_OK(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
@@ -555,12 +558,11 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
   CUDA_OK(cudaEventRecord(h->ev0, h->stream));
   // fork: the auxiliary streams wait for everything queued so far on the main stream
   CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
-  for (int i = 0; i < rchem_basis::kAuxStreams; ++i)
-    CUDA_OK(cudaStreamWaitEvent(h->aux[i], h->ev_fork, 0));
+  for (int i = 0; i < h->n_aux; ++i) CUDA_OK(cudaStreamWaitEvent(h->aux[i], h->ev_fork, 0));
   int next_stream = 0;
   auto pick_stream = [&]() {
     cudaStream_t s = h->aux[next_stream];
-    next_stream = (next_stream + 1) % rchem_basis::kAuxStreams;
+    next_stream = (next_stream + 1) % h->n_aux;
     return s;
   };
   for (const TaskTable& tt : h->tasks) {
@@ -621,7 +623,7 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
     }
   }
   // join: the main stream waits for every auxiliary stream
-  for (int i = 0; i < rchem_basis::kAuxStreams; ++i) {
+  for (int i = 0; i < h->n_aux; ++i) {
     CUDA_OK(cudaEventRecord(h->ev_join[i], h->aux[i]));
     CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_join[i], 0));
   }

@@ -319,6 +319,9 @@ __global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
 #ifndef RCHEM_BLK_T_SMALL
 #define RCHEM_BLK_T_SMALL 512
 #endif
+#ifndef RCHEM_BLK_PASSES
+#define RCHEM_BLK_PASSES 8
+#endif
 #ifndef RCHEM_BLK_MINB_SMALL
 #define RCHEM_BLK_MINB_SMALL 2
 #endif
@@ -330,7 +333,7 @@ template <int LA, int LB, int LC, int LD> struct BlockCfg {
   static constexpr bool kMedium = !kSmall && kTargets <= 18;
   static constexpr int kThreadsBlk = kSmall ? RCHEM_BLK_T_SMALL : 256;
   static constexpr int kMinBlocks = kSmall ? RCHEM_BLK_MINB_SMALL : (kMedium ? 2 : 1);
-  static constexpr int kKetsPerBlock = kThreadsBlk * 8;
+  static constexpr int kKetsPerBlock = kThreadsBlk * RCHEM_BLK_PASSES;
 };
 
 __device__ __forceinline__ void smem_add(double* addr, double v) { atomicAdd(addr, v); }
