@@ -509,15 +509,15 @@ int ensure_tasks(rchem_basis* h) {
       const bool rows_fit = tt.smem_bytes <= kMaxBlockSmem && info.threads > 0;
       // a bra pair is "heavy" when its ket prefix fills the block kernel's threads at least
       // kHeavyPasses times (the last, partial pass of a block idles most of its warps)
-      static const int kHeavyPasses = [] {
+      static const double kHeavyPasses = [] {  // tuning knob; 1 pass measured best (0.125..8)
         const char* e = std::getenv("RCHEM_HEAVY_PASSES");
-        return e ? std::max(1, atoi(e)) : 1;
+        return e ? std::max(0.01, atof(e)) : 1.0;
       }();
       std::vector<int> nq_light(B.npairs), hp;
       std::vector<long long> prefix_light(B.npairs + 1, 0), hblk(1, 0);
       for (int p = 0; p < B.npairs; ++p) {
         const int cut = tt.h_nq[p];
-        const bool heavy = rows_fit && cut >= kHeavyPasses * info.threads;
+        const bool heavy = rows_fit && cut >= (int)(kHeavyPasses * info.threads);
         nq_light[p] = heavy ? 0 : cut;
         prefix_light[p + 1] = prefix_light[p] + (nq_light[p] + 31) / 32;
         if (heavy) {
