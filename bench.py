@@ -407,10 +407,15 @@ def run_ours(args):
     }
     line["roofline"] = {
         "bound": "fp64", "achieved": achieved, "peak": peak_avg, "unit": "TFLOP/s",
-        "frac": achieved / peak_avg, "traffic": None,
+        "frac": achieved / peak_avg,
+        # DRAM bytes of one step (all ERI launches), from the committed ncu launch list
+        # profiles/r01_launch_summary_h2o96_631g_ref.txt (headline workload, 1 GPU); null for
+        # other workloads / GPU counts
+        "traffic": 4.14e9 if (args.workload == DEFAULT_WORKLOAD and world == 1) else None,
         "peak_source": "measured in this run: DFMA microbenchmark rchem_fp64_peak (avg of 10; "
                        f"best {peak_best:.2f}); MEASURED_PEAKS.json has no FP64 entry",
-        "kernel": "eri_kernel<la,lb,lc,ld,boys,JK> (all class instantiations of one step)",
+        "kernel": "eri_jk_block_kernel<la,lb,lc,ld,boys> + eri_kernel<..,JK> (all class "
+                  "instantiations of one step; the (ps|ss) block kernel is the largest share)",
         "kernel_ms_per_step": k_ms,
         "algorithmic_flops_per_step": flops,
         "flop_model": "SURVEY 8(d): sum over surviving quartets of K2_bra*K2_ket*P(class)+H(class)",
