@@ -273,3 +273,31 @@ def test_reference_equals_exact_past_cut(hostcheck):
             hostcheck.hostcheck_boys(1, 8, float(x), Fe)
             hostcheck.hostcheck_boys(2, 8, float(x), Fs)
             assert abs(Fs[m] / Fe[m] - 1) < 4e-15, (m, x)
+
+
+# ---- Basis Set Exchange JSON ingestion ---------------------------------------------
+def test_bse_json_ingestion(rc, geo):
+    from rchem_b200 import bse
+
+    z, x = geo.molecule(geo.WATER_CRAWFORD)
+    path = os.path.join(ROOT, "tests", "golden", "sto-3g.bse.json")
+    o, p, off, e, c, nrm = bse.cgtos_from_bse(path, z, x)
+    ref = rc.Basis.new(z, x, "STO-3G").export()
+    assert np.array_equal(o, ref[0]) and np.array_equal(p, ref[1]) and np.array_equal(off, ref[2])
+    # the BSE file carries more digits than the embedded 8-digit table
+    assert np.abs(e / ref[3] - 1).max() < 5e-7 and np.abs(c - ref[4]).max() < 5e-8
+    b = bse.basis_from_bse(open(path).read(), z, x)
+    assert len(b) == 7 and list(b.shells()[0]) == [0, 0, 1, 0, 0]
+    # a lone d shell and a general contraction: index by position, one CGTO set per row
+    custom = {"elements": {"8": {"electron_shells": [
+        {"function_type": "gto", "angular_momentum": [2], "exponents": ["0.8"], "coefficients": [["1.0"]]},
+        {"function_type": "gto", "angular_momentum": [0], "exponents": ["3.0", "0.5"],
+         "coefficients": [["0.4", "0.7"], ["-0.2", "1.0"]]}]}}}
+    b = bse.basis_from_bse(custom, [8], [[0.0, 0.0, 0.0]])
+    assert len(b) == 6 + 2 and list(b.shells()[0]) == [2, 0, 0]
+    with pytest.raises(ValueError):
+        bse.basis_from_bse({"elements": {"8": {"electron_shells": [
+            {"function_type": "gto_spherical", "angular_momentum": [2], "exponents": ["0.8"],
+             "coefficients": [["1.0"]]}]}}}, [8], [[0, 0, 0]])
+    with pytest.raises(KeyError):
+        bse.basis_from_bse(custom, [1], [[0, 0, 0]])
