@@ -40,11 +40,15 @@ template <int BOYS>
 static cudaError_t launch_block(const EriTask& task, unsigned grid, size_t smem,
                                 cudaStream_t stream) {
   auto kern = eri_jk_block_kernel<RCHEM_LA, RCHEM_LB, RCHEM_LC, RCHEM_LD, BOYS>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the opt-in limit is per device; remember what was configured for each
+  static size_t configured[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || smem > configured[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
   }
   kern<<<grid, BlockCfg<RCHEM_LA, RCHEM_LB, RCHEM_LC, RCHEM_LD>::kThreadsBlk, smem, stream>>>(task);
   return cudaGetLastError();
