@@ -255,7 +255,7 @@ struct rchem_basis {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // The tasks of one J/K (or tensor) build are independent kernels; they are spread over a
   // few auxiliary streams so the tail of one launch overlaps the head of the next.
-  static constexpr int kAuxStreams = 16;  // upper bound; RCHEM_STREAMS (default 12) are used
+  static constexpr int kAuxStreams = 16;  // upper bound; n_aux (6 or 12, RCHEM_STREAMS) are used
   int n_aux = 12;
   cudaStream_t aux[kAuxStreams] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kAuxStreams] = {};
@@ -350,6 +350,9 @@ int ensure_ready(rchem_basis* h) {
   CUDA_OK(cudaEventCreate(&h->ev0));
   CUDA_OK(cudaEventCreate(&h->ev1));
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  // measured: s/p-only bases like many streams (short, similar kernels); with d shells the
+  // register-heavy kernels compete and 6 is better
+  h->n_aux = h->shells.lmax >= 2 ? 6 : 12;
   if (const char* e = std::getenv("RCHEM_STREAMS"))
     h->n_aux = std::min((int)rchem_basis::kAuxStreams, std::max(1, atoi(e)));
   for (int i = 0; i < rchem_basis::kAuxStreams; ++i) {
@@ -409,6 +412,7 @@ int ensure_ready(rchem_basis* h) {
     t.same = 1;
     t.Qout = dQ;
     EriLaunchFn fn = find_launcher(bt.la, bt.lb, bt.la, bt.lb);
+    if (!fn) return fail(RCHEM_ERR_UNSUPPORTED_AM, "no kernel for this class in this build");
     const unsigned grid = (unsigned)((t.nwarps + kWarpsPerBlock - 1) / kWarpsPerBlock);
     CUDA_OK(fn(kBoysExact, kModeSchwarz, t, grid, h->stream));
     bt.Q.resize(bt.npairs);

@@ -104,10 +104,11 @@ __device__ __forceinline__ BraGeom load_bra_geom(const BatchView& bra, int p) {
 
 // BRA_SMEM: the bra pair's primitive pairs were staged in shared memory (block kernel);
 // otherwise they are read (warp-uniformly) from the SoA arrays.
-template <class C, int LA, int LB, int LC, int LD, int BOYS, bool BRA_SMEM>
+template <class C, int LA, int LB, int LC, int LD, int BOYS, bool BRA_SMEM, bool DETECT = false>
 __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const BraGeom& g,
                                                 const PrimPair* __restrict__ s_bra, int q,
-                                                double* __restrict__ out, int& bfC, int& bfD) {
+                                                double* __restrict__ out, int& bfC, int& bfD,
+                                                bool* needs_correction = nullptr) {
   constexpr int NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
   constexpr bool kUnroll = C::kOut <= 81;
   const double* gk = t.ket.geom + q;
@@ -127,7 +128,8 @@ __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const B
     const PrimPair pk = load_prim(t.ket, kk, q);
     for (int kb = 0; kb < K2b; ++kb) {
       if (BRA_SMEM) {
-        primitive_quartet<C, BOYS>(s_bra[kb], pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys, acc);
+        primitive_quartet<C, BOYS, DETECT>(s_bra[kb], pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys, acc,
+                                           needs_correction);
       } else {
         const PrimPair pb = load_prim(t.bra, kb, p);
         primitive_quartet<C, BOYS>(pb, pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys, acc);
@@ -465,12 +467,37 @@ eri_jk_block_kernel(const EriTask t) {
   }
   __syncthreads();
 
-  for (int it = tid; it < nk; it += T) {
-    const int q = kPartition ? s_list[it] : q0 + it;
+  // Shallow contractions (reference flavour): two passes instead of a reordering.  Pass 0
+  // evaluates every quartet with the converged Boys values only and merely DETECTS primitives
+  // that need the Fgamma truncation correction (a few % of the quartets, about one lane per
+  // warp); such quartets are not digested but queued, and pass 1 re-evaluates the queue with the
+  // full reference path, all lanes busy.
+  // (small classes only: for larger ones the second instantiation of the quartet code costs
+  // more registers and instruction cache than the dense pass saves)
+  constexpr bool kTwoPassClass = BOYS == kBoysReference && C::kTargets <= 9;
+  const bool kTwoPass = kTwoPassClass && !kPartition;
+  if (kTwoPass) {
+    if (tid == 0) s_cnt[0] = 0;
+    __syncthreads();
+  }
+  for (int pass = 0; pass < (kTwoPass ? 2 : 1); ++pass) {
+  const int n_items = (kTwoPass && pass == 1) ? s_cnt[0] : nk;
+  for (int it = tid; it < n_items; it += T) {
+    const int q = (kPartition || (kTwoPass && pass == 1)) ? s_list[it] : q0 + it;
     double out[C::kOut];
     int bfC, bfD;
-    const double scale =
-        shell_quartet<C, LA, LB, LC, LD, BOYS, true>(t, p, g, s_bra, q, out, bfC, bfD);
+    double scale;
+    if (kTwoPassClass && kTwoPass && pass == 0) {
+      bool dirty = false;
+      scale = shell_quartet<C, LA, LB, LC, LD, BOYS, true, kTwoPassClass>(
+          t, p, g, s_bra, q, out, bfC, bfD, &dirty);
+      if (dirty) {
+        s_list[atomicAdd(&s_cnt[0], 1)] = q;
+        continue;
+      }
+    } else {
+      scale = shell_quartet<C, LA, LB, LC, LD, BOYS, true>(t, p, g, s_bra, q, out, bfC, bfD);
+    }
 
     double jcd[NC * ND], kac[NA * NC], kad[NA * ND], kbc[NB * NC], kbd[NB * ND], Dcd[NC * ND];
 #pragma unroll
@@ -509,6 +536,8 @@ eri_jk_block_kernel(const EriTask t) {
     for (int i = 0; i < NB * NC; ++i) smem_add(Krow_b + (i / NC) * N + bfC + i % NC, kbc[i]);
 #pragma unroll
     for (int i = 0; i < NB * ND; ++i) smem_add(Krow_b + (i / ND) * N + bfD + i % ND, kbd[i]);
+  }
+  if (kTwoPass) __syncthreads();  // the queue is complete / pass 1 is done
   }
 
   // bra block of J: registers -> warp reduce -> one atomic per warp and component
