@@ -27,10 +27,23 @@
 namespace rchem {
 
 // launchers, one per class translation unit
-#define X(la, lb, lc, ld, tag)                                                        \
-  cudaError_t launch_eri_##tag(int, int, const EriTask&, unsigned, cudaStream_t);     \
-  cudaError_t launch_eri_block_##tag(int, const EriTask&, unsigned, size_t, cudaStream_t); \
-  EriBlockInfo block_info_##tag();
+// (one translation unit per class and Boys flavour: eri_class_tu.cu)
+#define X(la, lb, lc, ld, tag)                                                              \
+  cudaError_t launch_eri_##tag##_b0(int, const EriTask&, unsigned, cudaStream_t);           \
+  cudaError_t launch_eri_##tag##_b1(int, const EriTask&, unsigned, cudaStream_t);           \
+  cudaError_t launch_eri_block_##tag##_b0(const EriTask&, unsigned, size_t, cudaStream_t);  \
+  cudaError_t launch_eri_block_##tag##_b1(const EriTask&, unsigned, size_t, cudaStream_t);  \
+  EriBlockInfo block_info_##tag();                                                          \
+  static cudaError_t launch_eri_##tag(int boys, int mode, const EriTask& t, unsigned g,     \
+                                      cudaStream_t s) {                                     \
+    return boys == kBoysReference ? launch_eri_##tag##_b0(mode, t, g, s)                    \
+                                  : launch_eri_##tag##_b1(mode, t, g, s);                   \
+  }                                                                                         \
+  static cudaError_t launch_eri_block_##tag(int boys, const EriTask& t, unsigned g,         \
+                                            size_t smem, cudaStream_t s) {                  \
+    return boys == kBoysReference ? launch_eri_block_##tag##_b0(t, g, smem, s)              \
+                                  : launch_eri_block_##tag##_b1(t, g, smem, s);             \
+  }
 RCHEM_ERI_CLASSES(X)
 #undef X
 
