@@ -1,18 +1,23 @@
-// eri_kernel.cuh -- the sm_100a shell-quartet kernel, one instantiation per angular-momentum
-// class, Boys flavour and output mode.
+// eri_kernel.cuh -- the sm_100a shell-quartet kernels, instantiated per angular-momentum class
+// and Boys flavour.
 //
-// Work decomposition (DESIGN.md "kernel"):
+// Work decomposition:
 //   * a TASK is a pair of shell-pair batches (bra batch, ket batch); every pair of a batch has
-//     the same (la,lb) and the same number of primitive pairs K2, so all quartets of a task
-//     run the same straight-line code with the same trip counts;
+//     the same (la,lb) and the same number of (significant) primitive pairs K2, so all
+//     quartets of a task run the same straight-line code with the same trip counts;
 //   * ket pairs are sorted by Schwarz bound (descending), so the kets that survive screening
 //     against bra pair p are the prefix q < nq[p];
-//   * one WARP takes (bra pair p, 32 consecutive kets): bra data is warp-uniform (one
-//     broadcast load), ket data is read coalesced from [primitive][pair] SoA arrays;
 //   * one THREAD owns one contracted shell quartet: loops over K2_ket x K2_bra primitive
-//     quartets, accumulating the [e0|f0] VRR targets in registers, then HRR, then either
-//     digests the block into J/K (8-fold symmetry, 6 updates per integral), scatters it into
-//     the dense tensor, or reduces it to a Schwarz bound.
+//     quartets, accumulating the [e0|f0] VRR targets in registers, then HRR, then digests the
+//     block into J/K (8-fold symmetry, 6 updates per integral), writes the canonical tensor
+//     element, or reduces it to a Schwarz bound;
+//   * eri_kernel (warp kernel): one WARP per (bra pair p, 32 consecutive kets) -- bra data
+//     warp-uniform, ket data coalesced from [primitive][pair] SoA arrays.  Used for the dense
+//     tensor, the Schwarz bounds and the J/K of "light" bra pairs;
+//   * eri_jk_block_kernel: one BLOCK per (bra pair, <= 8 T kets) for "heavy" bra pairs, with the
+//     bra pair's D rows and K accumulators in shared memory, and (reference Boys flavour)
+//     either a regime-sorted ket order or a dense second pass for quartets that need the
+//     Fgamma truncation correction.
 // All arithmetic is IEEE fp64 on the FP64 pipe.
 //
 // Reference: the loops this replaces are basis.rs:383-428 (JK_direct) and basis.rs:430-460
