@@ -201,19 +201,32 @@ __global__ void tensor_fill_kernel(double* __restrict__ I, int N, int ns,
 // JK_inmem (basis.rs:462-484) in ONE pass over the tensor: element I[i][j][k][l] feeds
 // J[i][j] (with D[k][l]) and K[i][k] (with D[j][l]).  One block per (i,j) row of N^2 values;
 // one warp per k sums over l.  HBM-bound: 8 N^4 bytes read once.
-__global__ void jk_inmem_kernel(const double* __restrict__ I, const double* __restrict__ D,
-                                double* __restrict__ JK, int N) {
+// U = independent streaming loads in flight per lane (the tensor is read exactly once);
+// out-of-range slots are predicated off instead of peeled.
+template <int U>
+__global__ void __launch_bounds__(256) jk_inmem_kernel(const double* __restrict__ I,
+                                                       const double* __restrict__ D,
+                                                       double* __restrict__ JK, int N) {
   const size_t nn = (size_t)N * N;
   const int i = blockIdx.x / N, j = blockIdx.x % N;
   const double* row = I + (size_t)blockIdx.x * nn;
+  const double* Dj = D + (size_t)j * N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   double jsum = 0.0;
   for (int k = warp; k < N; k += nwarps) {
+    const double* rk = row + (size_t)k * N;
+    const double* Dk = D + (size_t)k * N;
     double ks = 0.0;
-    for (int l = lane; l < N; l += 32) {
-      const double v = row[(size_t)k * N + l];
-      jsum = fma(v, D[(size_t)k * N + l], jsum);
-      ks = fma(v, D[(size_t)j * N + l], ks);
+    for (int l = lane; l < N; l += 32 * U) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = (l + 32 * u < N) ? __ldcs(rk + l + 32 * u) : 0.0;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (l + 32 * u < N) {
+          jsum = fma(v[u], __ldg(Dk + l + 32 * u), jsum);
+          ks = fma(v[u], __ldg(Dj + l + 32 * u), ks);
+        }
     }
     ks = warp_sum(ks);
     if (lane == 0) atomicAdd(JK + nn + (size_t)i * N + k, ks);
@@ -928,7 +941,11 @@ int rchem_jk_inmem_device(int n, const double* I_dev, const double* D_dev, doubl
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const size_t nn = (size_t)n * n;
   CUDA_OK(cudaMemsetAsync(JK_dev, 0, 2 * nn * sizeof(double), s));
-  jk_inmem_kernel<<<(unsigned)nn, 256, 0, s>>>(I_dev, D_dev, JK_dev, n);
+  // depth of the load pipeline: enough slots to cover a k-row in one or two sweeps
+  const int slots = (n + 31) / 32;
+  if (slots <= 2) jk_inmem_kernel<2><<<(unsigned)nn, 256, 0, s>>>(I_dev, D_dev, JK_dev, n);
+  else if (slots <= 4) jk_inmem_kernel<4><<<(unsigned)nn, 256, 0, s>>>(I_dev, D_dev, JK_dev, n);
+  else jk_inmem_kernel<8><<<(unsigned)nn, 256, 0, s>>>(I_dev, D_dev, JK_dev, n);
   CUDA_OK(cudaGetLastError());
   return RCHEM_OK;
 }
