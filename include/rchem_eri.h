@@ -83,6 +83,10 @@ int64_t rchem_ijkl2intindex(int64_t i, int64_t j, int64_t k, int64_t l);
 #define RCHEM_OPT_PRIM_EPS 4    /* drop primitive pairs with |c_a c_b N_a N_b exp(..)/zeta| below
                                    this (default 1e-20: < 1e-15 per integral; 0 keeps all);
                                    before the first compute call                               */
+#define RCHEM_OPT_FAR_SCHED 5   /* 1 (default): J/K kernels prove shell quartets far-field from the
+                                   pairs' bounding spheres and evaluate those by the point-
+                                   multipole form; 0: every quartet through the general code
+                                   (same results to ~1e-15; a tuning / cross-check knob)        */
 int rchem_set_option(rchem_basis* b, int key, double value);
 double rchem_get_option(const rchem_basis* b, int key);
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream).  The value is used as

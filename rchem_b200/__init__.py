@@ -23,10 +23,11 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librchem_b200.so")
+# RCHEM_B200_LIB: development only (A/B timing of two builds of the same library)
+LIB_PATH = os.environ.get("RCHEM_B200_LIB") or os.path.join(_HERE, "librchem_b200.so")
 
 BOYS_REFERENCE, BOYS_EXACT = 0, 1
-OPT_BOYS, OPT_SCHWARZ_TAU, OPT_DEVICE, OPT_PRIM_EPS = 1, 2, 3, 4
+OPT_BOYS, OPT_SCHWARZ_TAU, OPT_DEVICE, OPT_PRIM_EPS, OPT_FAR_SCHED = 1, 2, 3, 4, 5
 
 
 class RchemError(RuntimeError):
@@ -203,6 +204,10 @@ class Basis:
     def set_prim_eps(self, eps):
         """Primitive-pair prefactor cutoff (default 1e-20; 0 keeps every primitive pair)."""
         _check(_lib.rchem_set_option(self._h, OPT_PRIM_EPS, float(eps)))
+
+    def set_far_sched(self, on):
+        """Far-field scheduling of the J/K kernels (default on; off = general code only)."""
+        _check(_lib.rchem_set_option(self._h, OPT_FAR_SCHED, 1.0 if on else 0.0))
 
     def set_device(self, ordinal):
         _check(_lib.rchem_set_option(self._h, OPT_DEVICE, float(ordinal)))

@@ -33,6 +33,8 @@ namespace rchem {
   cudaError_t launch_eri_##tag##_b1(int, const EriTask&, unsigned, cudaStream_t);           \
   cudaError_t launch_eri_block_##tag##_b0(const EriTask&, unsigned, size_t, cudaStream_t);  \
   cudaError_t launch_eri_block_##tag##_b1(const EriTask&, unsigned, size_t, cudaStream_t);  \
+  cudaError_t launch_eri_light_##tag##_b0(const EriTask&, unsigned, size_t, cudaStream_t);  \
+  cudaError_t launch_eri_light_##tag##_b1(const EriTask&, unsigned, size_t, cudaStream_t);  \
   EriBlockInfo block_info_##tag();                                                          \
   static cudaError_t launch_eri_##tag(int boys, int mode, const EriTask& t, unsigned g,     \
                                       cudaStream_t s) {                                     \
@@ -43,6 +45,11 @@ namespace rchem {
                                             size_t smem, cudaStream_t s) {                  \
     return boys == kBoysReference ? launch_eri_block_##tag##_b0(t, g, smem, s)              \
                                   : launch_eri_block_##tag##_b1(t, g, smem, s);             \
+  }                                                                                         \
+  static cudaError_t launch_eri_light_##tag(int boys, const EriTask& t, unsigned g,         \
+                                            size_t smem, cudaStream_t s) {                  \
+    return boys == kBoysReference ? launch_eri_light_##tag##_b0(t, g, smem, s)              \
+                                  : launch_eri_light_##tag##_b1(t, g, smem, s);             \
   }
 RCHEM_ERI_CLASSES(X)
 #undef X
@@ -98,6 +105,13 @@ static EriBlockLaunchFn find_block_launcher(int la, int lb, int lc, int ld, EriB
 #undef X
   return nullptr;
 }
+static EriLightLaunchFn find_light_launcher(int la, int lb, int lc, int ld) {
+#define X(a, b, c, d, tag) \
+  if (la == a && lb == b && lc == c && ld == d) return launch_eri_light_##tag;
+  RCHEM_ERI_CLASSES(X)
+#undef X
+  return nullptr;
+}
 // dynamic shared memory the block kernel may use (227 KB per CTA on sm_100, minus slack)
 static constexpr size_t kMaxBlockSmem = 220 * 1024;
 
@@ -129,6 +143,10 @@ struct TaskTable {
   int* d_hp = nullptr;
   long long* d_hblk_prefix = nullptr;
   size_t smem_bytes = 0;
+  // light bra pairs with >= 1 ket, for the warp-per-bra-pair kernel (0 = use the chunk kernel)
+  int* d_lp = nullptr;
+  int nlight = 0, light_cap = 0;
+  size_t light_smem = 0;
 };
 
 // D blocks of every shell pair of a batch, pair-major packed: Dp[ab][p] = D[bfA+a][bfB+b]
@@ -262,6 +280,10 @@ struct rchem_basis {
   double tau = 0.0;
   double prim_eps = kPrimPairEps;
   int device = 0;
+  int far_sched = [] {  // RCHEM_OPT_FAR_SCHED; the environment sets the default (tuning)
+    const char* e = std::getenv("RCHEM_FAR");
+    return e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }();
   // device state
   bool ready = false;
   cudaStream_t own_stream = nullptr;
@@ -295,7 +317,7 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   const int np = bt.npairs;
   bt.stride = (np + 31) / 32 * 32;
   const size_t st = bt.stride;
-  std::vector<double> prim(6 * (size_t)bt.K2 * st, 0.0), geom(6 * st, 0.0);
+  std::vector<double> prim(kPrimFields * (size_t)bt.K2 * st, 0.0), geom(kGeomFields * st, 0.0);
   std::vector<int> idx(3 * st, 0);
   std::vector<PrimPair> pps;
   std::vector<int> shA(np), shB(np);
@@ -310,21 +332,25 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
     build_significant_prim_pairs(A, B, h->prim_eps, &pps);  // pps.size() == bt.K2 by construction
     for (int k = 0; k < bt.K2; ++k) {
       const PrimPair& pp = pps[k];
-      const double f[6] = {pp.zeta, pp.rzeta, pp.Px, pp.Py, pp.Pz, pp.pref};
-      for (int c = 0; c < 6; ++c) prim[((size_t)c * bt.K2 + k) * st + s] = f[c];
+      const double f[kPrimFields] = {pp.zeta, pp.rzeta, pp.Px, pp.Py, pp.Pz, pp.pref, pp.pfar};
+      for (int c = 0; c < kPrimFields; ++c) prim[((size_t)c * bt.K2 + k) * st + s] = f[c];
     }
+    const PairBound pb = bound_prim_pairs(pps);
     for (int d = 0; d < 3; ++d) {
       geom[d * st + s] = A.ctr[d];
       geom[(3 + d) * st + s] = A.ctr[d] - B.ctr[d];
+      geom[(6 + d) * st + s] = pb.M[d];
     }
+    geom[9 * st + s] = pb.rad;
+    geom[10 * st + s] = pb.zmin;
     idx[s] = A.bf0;
     idx[st + s] = B.bf0;
     idx[2 * st + s] = (bt.shA[src] == bt.shB[src]) ? 1 : 0;
   }
   // padding slots replicate pair 0 so stray reads stay finite
   for (int s = np; s < (int)st; ++s) {
-    for (size_t c = 0; c < 6 * (size_t)bt.K2; ++c) prim[c * st + s] = prim[c * st];
-    for (int c = 0; c < 6; ++c) geom[c * st + s] = geom[c * st];
+    for (size_t c = 0; c < kPrimFields * (size_t)bt.K2; ++c) prim[c * st + s] = prim[c * st];
+    for (int c = 0; c < kGeomFields; ++c) geom[c * st + s] = geom[c * st];
     for (int c = 0; c < 3; ++c) idx[c * st + s] = idx[c * st];
   }
   bt.shA.swap(shA);
@@ -355,6 +381,7 @@ void fill_common(const rchem_basis* h, EriTask* t) {
   t->boys.delta.thr = h->d_delta_thr;
   t->boys.delta.rows = h->d_delta_rows;
   t->nranks = 1;
+  t->far_sched = h->far_sched;
   for (int l = 0; l < 3; ++l)
     for (int k = 0; k < 6; ++k) t->compscale[l][k] = (l <= h->shells.lmax) ? h->shells.compscale[l][k] : 1.0;
 }
@@ -492,6 +519,7 @@ void free_tasks(rchem_basis* h) {
     if (t.d_prefix_light) cudaFree(t.d_prefix_light);
     if (t.d_nq_light) cudaFree(t.d_nq_light);
     if (t.d_hp) cudaFree(t.d_hp);
+    if (t.d_lp) cudaFree(t.d_lp);
     if (t.d_hblk_prefix) cudaFree(t.d_hblk_prefix);
   }
   h->tasks.clear();
@@ -558,6 +586,27 @@ int ensure_tasks(rchem_basis* h) {
         }
       }
       tt.nwarps_light = prefix_light[B.npairs];
+      // The light pairs go to the warp-per-bra-pair kernel when the class has one (the block
+      // kernel's classes) and a warp's ket list fits its shared-memory slice; otherwise to
+      // the chunk (warp-per-32-kets) kernel.
+      {
+        std::vector<int> lp;
+        int cap = 0;
+        for (int p = 0; p < B.npairs; ++p)
+          if (nq_light[p] > 0) { lp.push_back(p); cap = std::max(cap, nq_light[p]); }
+        const size_t per_warp = (((size_t)B.K2 * sizeof(PrimPair) + (size_t)cap * sizeof(int)) + 7) & ~(size_t)7;
+        static const bool kLightKernel = [] {
+          const char* e = std::getenv("RCHEM_LIGHT");
+          return e ? atoi(e) != 0 : true;
+        }();
+        if (kLightKernel && info.threads > 0 && !lp.empty() && per_warp * kWarpsPerBlock <= 40 * 1024) {
+          tt.nlight = (int)lp.size();
+          tt.light_cap = cap;
+          tt.light_smem = per_warp * kWarpsPerBlock;
+          CUDA_OK(cudaMalloc(&tt.d_lp, lp.size() * sizeof(int)));
+          CUDA_OK(cudaMemcpy(tt.d_lp, lp.data(), lp.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
+      }
       tt.nheavy = (int)hp.size();
       tt.nblocks_heavy = hblk.back();
       CUDA_OK(cudaMalloc(&tt.d_prefix_light, prefix_light.size() * sizeof(long long)));
@@ -625,7 +674,19 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
     const bool split = mode == kModeJK;
     // --- warp kernel (everything in tensor mode; the light bra pairs in J/K mode) ---
     const long long nwarps = split ? tt.nwarps_light : tt.nwarps;
-    if (nwarps > 0) {
+    if (split && tt.nlight > 0) {
+      // --- warp-per-bra-pair kernel (light bra pairs, J/K mode) ---
+      EriLightLaunchFn lfn = find_light_launcher(B.la, B.lb, K.la, K.lb);
+      t.nq = tt.d_nq;
+      t.lp = tt.d_lp;
+      t.nlight = tt.nlight;
+      t.light_cap = tt.light_cap;
+      const long long nblocks = ((long long)tt.nlight + kWarpsPerBlock - 1) / kWarpsPerBlock;
+      const long long mine = my_blocks(nblocks);
+      CUDA_OK(lfn(h->boys, t, (unsigned)mine, tt.light_smem, pick_stream()));
+      if (mine > 0) st.launches += 1;
+      account(tt.nquartets_light * (double)mine / (double)nblocks);
+    } else if (nwarps > 0) {
       t.warp_prefix = split ? tt.d_prefix_light : tt.d_prefix;
       t.nq = split ? tt.d_nq_light : tt.d_nq;
       t.nwarps = nwarps;
@@ -833,6 +894,10 @@ int rchem_set_option(rchem_basis* h, int key, double value) {
       if (!(value >= 0.0)) return fail(RCHEM_ERR_INVALID_ARG, "prim_eps must be >= 0");
       h->prim_eps = value;
       return RCHEM_OK;
+    case RCHEM_OPT_FAR_SCHED:
+      if (value != 0.0 && value != 1.0) return fail(RCHEM_ERR_INVALID_ARG, "far_sched must be 0 or 1");
+      h->far_sched = (int)value;
+      return RCHEM_OK;
   }
   return fail(RCHEM_ERR_INVALID_ARG, "unknown option");
 }
@@ -844,6 +909,7 @@ double rchem_get_option(const rchem_basis* h, int key) {
     case RCHEM_OPT_SCHWARZ_TAU: return h->tau;
     case RCHEM_OPT_DEVICE: return h->device;
     case RCHEM_OPT_PRIM_EPS: return h->prim_eps;
+    case RCHEM_OPT_FAR_SCHED: return h->far_sched;
   }
   return std::numeric_limits<double>::quiet_NaN();
 }

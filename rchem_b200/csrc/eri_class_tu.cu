@@ -59,6 +59,20 @@ cudaError_t RCHEM_CAT(launch_eri_block_, RCHEM_SUFFIX)(const EriTask& task, unsi
   }
 }
 
+// warp-per-bra-pair kernel for the light bra pairs (same classes as the block kernel)
+cudaError_t RCHEM_CAT(launch_eri_light_, RCHEM_SUFFIX)(const EriTask& task, unsigned grid,
+                                                       size_t smem, cudaStream_t stream) {
+  if (grid == 0) return cudaSuccess;
+  if constexpr (kHasBlockKernel) {
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;  // (the engine keeps it below)
+    eri_jk_light_kernel<RCHEM_LA, RCHEM_LB, RCHEM_LC, RCHEM_LD, RCHEM_BOYS>
+        <<<grid, kThreads, smem, stream>>>(task);
+    return cudaGetLastError();
+  } else {
+    return cudaErrorNotSupported;
+  }
+}
+
 #if RCHEM_BOYS == 0
 EriBlockInfo RCHEM_CAT(block_info_, RCHEM_TAG)() {
   using Cfg = BlockCfg<RCHEM_LA, RCHEM_LB, RCHEM_LC, RCHEM_LD>;

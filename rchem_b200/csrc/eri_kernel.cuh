@@ -34,9 +34,12 @@ constexpr int kWarpsPerBlock = kThreads / 32;
 
 enum EriMode : int { kModeJK = 0, kModeTensor = 1, kModeSchwarz = 2 };
 
-// Device view of one shell-pair batch.  prim holds six [K2][stride] arrays in the order
-// zeta, rzeta, Px, Py, Pz, pref; geom holds six [stride] arrays Ax,Ay,Az,ABx,ABy,ABz;
+// Device view of one shell-pair batch.  prim holds kPrimFields [K2][stride] arrays in the order
+// zeta, rzeta, Px, Py, Pz, pref, pfar; geom holds kGeomFields [stride] arrays Ax,Ay,Az,
+// ABx,ABy,ABz, then the pair's bounding data Mx,My,Mz,rad,zmin (pair_build.h PairBound);
 // idx holds three [stride] int arrays bfA, bfB, diag.
+constexpr int kPrimFields = 7;
+constexpr int kGeomFields = 11;
 struct BatchView {
   const double* prim;
   const double* geom;
@@ -55,6 +58,7 @@ struct EriTask {
   long long nwarps;              // warp_prefix[bra.npairs]
   int same;                      // bra batch == ket batch (then ket q <= p, and p==q is diagonal)
   int rank, nranks;              // multi-GPU: this process takes blocks b with b % nranks == rank
+  int far_sched;                 // 1: prove-and-route far-field quartets (0 = tuning/debug)
   int N;                         // number of basis functions
   const double* D;               // [N][N] density (symmetric)            kModeJK
   double* Kh;                    // [N][N] half-accumulated K             kModeJK
@@ -63,6 +67,10 @@ struct EriTask {
   const long long* hblk_prefix;  // [nheavy+1] running block count
   long long nblocks_heavy;
   int nheavy;
+  // warp-per-bra-pair J/K kernel (eri_jk_light_kernel): "light" bra pairs with >= 1 ket
+  const int* lp;                 // [nlight]   bra pair index of light entry
+  int nlight;
+  int light_cap;                 // list capacity per warp (upper bound of a light pair's nq)
   double* I;                     // [N]^4 dense tensor                    kModeTensor
   double* Qout;                  // [bra.npairs] Schwarz bounds           kModeSchwarz
   BoysTabs boys;                 // Boys tables (exact grid of this class's L, reference tables)
@@ -79,6 +87,7 @@ __device__ __forceinline__ PrimPair load_prim(const BatchView& b, int k, int p) 
   pp.Py = __ldg(base + 3 * fs);
   pp.Pz = __ldg(base + 4 * fs);
   pp.pref = __ldg(base + 5 * fs);
+  pp.pfar = __ldg(base + 6 * fs);  // (fields a caller does not use are dead loads, removed)
   return pp;
 }
 
@@ -109,11 +118,11 @@ __device__ __forceinline__ BraGeom load_bra_geom(const BatchView& bra, int p) {
 
 // BRA_SMEM: the bra pair's primitive pairs were staged in shared memory (block kernel);
 // otherwise they are read (warp-uniformly) from the SoA arrays.
-template <class C, int LA, int LB, int LC, int LD, int BOYS, bool BRA_SMEM, bool DETECT = false>
+// FAR: the caller has proved every primitive quartet far-field (primitive_quartet_far).
+template <class C, int LA, int LB, int LC, int LD, int BOYS, bool BRA_SMEM, bool FAR = false>
 __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const BraGeom& g,
                                                 const PrimPair* __restrict__ s_bra, int q,
-                                                double* __restrict__ out, int& bfC, int& bfD,
-                                                bool* needs_correction = nullptr) {
+                                                double* __restrict__ out, int& bfC, int& bfD) {
   constexpr int NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
   constexpr bool kUnroll = C::kOut <= 81;
   const double* gk = t.ket.geom + q;
@@ -132,9 +141,10 @@ __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const B
   for (int kk = 0; kk < K2k; ++kk) {
     const PrimPair pk = load_prim(t.ket, kk, q);
     for (int kb = 0; kb < K2b; ++kb) {
-      if (BRA_SMEM) {
-        primitive_quartet<C, BOYS, DETECT>(s_bra[kb], pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys, acc,
-                                           needs_correction);
+      if (FAR) {
+        primitive_quartet_far<C>(s_bra[kb], pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, acc);
+      } else if (BRA_SMEM) {
+        primitive_quartet<C, BOYS>(s_bra[kb], pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys, acc);
       } else {
         const PrimPair pb = load_prim(t.bra, kb, p);
         primitive_quartet<C, BOYS>(pb, pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys, acc);
@@ -345,10 +355,38 @@ template <int LA, int LB, int LC, int LD> struct BlockCfg {
 
 __device__ __forceinline__ void smem_add(double* addr, double v) { atomicAdd(addr, v); }
 
-// Boys argument of the leading primitive pairs from which a quartet is scheduled with the
-// far-field group (kBoysXMax plus a margin for the tighter primitives)
-constexpr double kFarSplitX = 56.0;
-constexpr int kPartitionMinPrims = 16;
+// A shell quartet is scheduled as far-field when the bounding spheres of its two shell pairs
+// prove x >= kFarProvenX for every primitive quartet (boys_exact switches to the asymptotic
+// form at kBoysXMax; the far-only code never looks at x again, so the proof must hold).
+constexpr double kFarProvenX = (double)kBoysXMax;
+
+
+// Scheduling regime of shell quartet (bra pair | ket pair q) from the pairs' bounding data
+// (pair_build.h PairBound): 0 = PROVED far-field (every primitive quartet has x >= 48),
+// 1 = Boys grid, proved free of the Fgamma correction, 2 = may need the correction
+// (reference flavour only; otherwise everything not far is 1).
+struct BraBound { double Mx, My, Mz, rad, zmin; };
+__device__ __forceinline__ BraBound load_bra_bound(const BatchView& bra, int p) {
+  const double* gb = bra.geom + p;
+  const int sb = bra.stride;
+  return BraBound{__ldg(gb + 6 * sb), __ldg(gb + 7 * sb), __ldg(gb + 8 * sb), __ldg(gb + 9 * sb),
+                  __ldg(gb + 10 * sb)};
+}
+template <int REGIMES>
+__device__ __forceinline__ int quartet_regime(const BraBound& b, const BatchView& ket, int q,
+                                              double xcorr, int far_on) {
+  const double* gk = ket.geom + q;
+  const int sk = ket.stride;
+  const double dx = b.Mx - __ldg(gk + 6 * sk), dy = b.My - __ldg(gk + 7 * sk),
+               dz = b.Mz - __ldg(gk + 8 * sk);
+  const double rr = b.rad + __ldg(gk + 9 * sk), zk = __ldg(gk + 10 * sk);
+  const double d2c = dx * dx + dy * dy + dz * dz;
+  const double dmin = rr > 0.0 ? sqrt(d2c) - rr : 1.0;  // (rr == 0: d^2 = d2c, no square root)
+  const double d2 = rr > 0.0 ? dmin * dmin : d2c;
+  const double lhs = b.zmin * zk * d2, zs = b.zmin + zk;  // x_min >= X  <=>  lhs >= X (zb + zk)
+  if (far_on && dmin > 0.0 && lhs >= kFarProvenX * zs) return 0;
+  return (REGIMES == 3 && !(dmin > 0.0 && lhs >= xcorr * zs)) ? 2 : 1;
+}
 
 template <int LA, int LB, int LC, int LD, int BOYS>
 __global__ void __launch_bounds__(BlockCfg<LA, LB, LC, LD>::kThreadsBlk,
@@ -358,6 +396,8 @@ eri_jk_block_kernel(const EriTask t) {
   constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
   constexpr bool kUnroll = C::kOut <= 81;
   constexpr int T = BlockCfg<LA, LB, LC, LD>::kThreadsBlk;
+  // regimes a block sorts its kets into: far-field (proved), grid, grid + Fgamma correction
+  constexpr int kRegimes = BOYS == kBoysReference ? 3 : 2;
   extern __shared__ double smem[];
   __shared__ int s_info[3];
   __shared__ int s_cnt[3];
@@ -381,6 +421,7 @@ eri_jk_block_kernel(const EriTask t) {
     s_info[1] = q0;
     s_info[2] = min(nq, q0 + per);
   }
+  if (tid < 3) s_cnt[tid] = 0;
   __syncthreads();
   const int p = s_info[0], q0 = s_info[1], q1 = s_info[2];
   const int N = t.N, sb = t.bra.stride, sk = t.ket.stride;
@@ -409,59 +450,45 @@ eri_jk_block_kernel(const EriTask t) {
     Dab[i] = __ldg(t.bra.Dp + (size_t)i * sb + p);
     jab[i] = 0.0;
   }
-  // Scheduling of this block's kets (reference Boys flavour only).  Lanes of a warp see
-  // unrelated Boys arguments, and the three regimes cost very differently: far field
-  // (x >= 48: a reciprocal square root), grid (Taylor expansion), and grid + truncation
-  // correction (x below ref_exact_from(L), a few % of the quartets).  Left in list order,
-  // almost every warp contains one lane of the expensive regime and pays for it with 31 idle
-  // lanes.  The kets are therefore reordered in shared memory into [far | grid | corrected],
-  // classified by the Boys argument of the most diffuse primitive pairs (stored first), so
-  // that warps work on one regime.  Misclassified primitives are still evaluated correctly;
-  // the split only decides which lanes run together.  With the exact flavour the reordering
-  // was measured to cost more (scattered ket reads) than it saves, so it is skipped.
+
+  // Regime scheduling of this block's kets.  89 % of the primitive quartets of a large
+  // cluster are far-field (x >= 48: point-multipole form, no Boys table), 8 % need the Boys
+  // grid and -- reference flavour -- 3 % the Fgamma truncation correction; but in list
+  // (Schwarz) order nearly every warp holds a lane of each regime and pays for all three.
+  // The block therefore sorts its kets in shared memory into [far | grid | corrected]:
+  //   * far: PROVED from the pairs' bounding data (centre M, radius rad, most diffuse
+  //     exponent zmin): rho(zmin_b, zmin_k) (|M_b - M_k| - rad_b - rad_k)^2 >= 48 bounds every
+  //     primitive quartet's x from below.  These run the far-only code (primitive_quartet_far);
+  //   * grid / corrected: the general code, which handles any x; the split (same lower bound
+  //     of x against ref_exact_from(L)) only decides which lanes run together.
   int* s_list = reinterpret_cast<int*>(s_bra + t.bra.K2);  // [q1 - q0]
   const int nk = q1 - q0;
-  // ... and it only pays when a quartet carries enough primitive work to amortise the two
-  // classification passes and the scattered ket reads (measured: deep contractions gain
-  // 10 %, single-primitive quartets lose 2 %).
-  const bool kPartition = BOYS == kBoysReference && t.bra.K2 * t.ket.K2 >= kPartitionMinPrims;
-  if (kPartition) {
-    if (tid < 3) s_cnt[tid] = 0;
-    __syncthreads();
-    const PrimPair b0 = s_bra[0];
-    const size_t fs = (size_t)t.ket.K2 * sk;
+  {
+    const BraBound bb = load_bra_bound(t.bra, p);
     const double xcorr = ref_exact_from(C::kL) + 2.0;
-    unsigned cls_bits = 0;  // 2 bits per pass: 0 far, 1 grid, 2 corrected
+    unsigned cls_bits = 0;  // 2 bits per pass: 0 far, 1 grid, 2 corrected, 3 none
     int pass = 0;
     for (int base = 0; base < nk; base += T, ++pass) {
       const int i = base + tid;
-      int cls = 3;  // invalid
-      if (i < nk) {
-        const double* kp = t.ket.prim + (q0 + i);  // primitive pair 0 (most diffuse) of ket q0+i
-        const double eta = __ldg(kp);
-        const double dx = b0.Px - __ldg(kp + 2 * fs), dy = b0.Py - __ldg(kp + 3 * fs),
-                     dz = b0.Pz - __ldg(kp + 4 * fs);
-        const double x0 = b0.zeta * eta / (b0.zeta + eta) * (dx * dx + dy * dy + dz * dz);
-        cls = x0 >= kFarSplitX ? 0 : (x0 >= xcorr ? 1 : 2);
-      }
+      const int cls = i < nk ? quartet_regime<kRegimes>(bb, t.ket, q0 + i, xcorr, t.far_sched) : 3;
       cls_bits |= (unsigned)cls << (2 * pass);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+      for (int c = 0; c < kRegimes; ++c) {
         const unsigned m = __ballot_sync(0xffffffffu, cls == c);
         if (lane == 0 && m) atomicAdd(&s_cnt[c], __popc(m));
       }
     }
     __syncthreads();
-    const int n_far = s_cnt[0], n_grid = s_cnt[1];
+    const int n0 = s_cnt[0], n1 = s_cnt[1];
     __syncthreads();
-    if (tid < 3) s_cnt[tid] = tid == 0 ? 0 : (tid == 1 ? n_far : n_far + n_grid);  // write cursors
+    if (tid == 0) { s_info[0] = n0; s_cnt[0] = 0; s_cnt[1] = n0; s_cnt[2] = n0 + n1; }  // cursors
     __syncthreads();
     pass = 0;
     for (int base = 0; base < nk; base += T, ++pass) {
       const int i = base + tid;
       const int cls = (cls_bits >> (2 * pass)) & 3;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+      for (int c = 0; c < kRegimes; ++c) {
         const unsigned m = __ballot_sync(0xffffffffu, cls == c);
         int at = 0;
         if (lane == 0 && m) at = atomicAdd(&s_cnt[c], __popc(m));
@@ -471,39 +498,10 @@ eri_jk_block_kernel(const EriTask t) {
     }
   }
   __syncthreads();
+  const int n_far = s_info[0];
 
-  // Shallow contractions (reference flavour): two passes instead of a reordering.  Pass 0
-  // evaluates every quartet with the converged Boys values only and merely DETECTS primitives
-  // that need the Fgamma truncation correction (a few % of the quartets, about one lane per
-  // warp); such quartets are not digested but queued, and pass 1 re-evaluates the queue with the
-  // full reference path, all lanes busy.
-  // (small classes only: for larger ones the second instantiation of the quartet code costs
-  // more registers and instruction cache than the dense pass saves)
-  constexpr bool kTwoPassClass = BOYS == kBoysReference && C::kTargets <= 9;
-  const bool kTwoPass = kTwoPassClass && !kPartition;
-  if (kTwoPass) {
-    if (tid == 0) s_cnt[0] = 0;
-    __syncthreads();
-  }
-  for (int pass = 0; pass < (kTwoPass ? 2 : 1); ++pass) {
-  const int n_items = (kTwoPass && pass == 1) ? s_cnt[0] : nk;
-  for (int it = tid; it < n_items; it += T) {
-    const int q = (kPartition || (kTwoPass && pass == 1)) ? s_list[it] : q0 + it;
-    double out[C::kOut];
-    int bfC, bfD;
-    double scale;
-    if (kTwoPassClass && kTwoPass && pass == 0) {
-      bool dirty = false;
-      scale = shell_quartet<C, LA, LB, LC, LD, BOYS, true, kTwoPassClass>(
-          t, p, g, s_bra, q, out, bfC, bfD, &dirty);
-      if (dirty) {
-        s_list[atomicAdd(&s_cnt[0], 1)] = q;
-        continue;
-      }
-    } else {
-      scale = shell_quartet<C, LA, LB, LC, LD, BOYS, true>(t, p, g, s_bra, q, out, bfC, bfD);
-    }
-
+  // digestion of one evaluated shell quartet (bra pair p | ket pair q) into J and K
+  auto digest = [&](int q, const double* __restrict__ out, double scale, int bfC, int bfD) {
     double jcd[NC * ND], kac[NA * NC], kad[NA * ND], kbc[NB * NC], kbd[NB * ND], Dcd[NC * ND];
 #pragma unroll
     for (int i = 0; i < NC * ND; ++i) { jcd[i] = 0.0; Dcd[i] = __ldg(t.ket.Dp + (size_t)i * sk + q); }
@@ -541,8 +539,27 @@ eri_jk_block_kernel(const EriTask t) {
     for (int i = 0; i < NB * NC; ++i) smem_add(Krow_b + (i / NC) * N + bfC + i % NC, kbc[i]);
 #pragma unroll
     for (int i = 0; i < NB * ND; ++i) smem_add(Krow_b + (i / ND) * N + bfD + i % ND, kbd[i]);
+  };
+
+  // Every thread walks the sorted list with stride T: far items first (all warps together in
+  // the early passes), then the general ones -- the per-thread item count is what it would be
+  // unsorted, so the block stays balanced.
+  int it = tid;
+  for (; it < n_far; it += T) {
+    const int q = s_list[it];
+    double out[C::kOut];
+    int bfC, bfD;
+    const double scale =
+        shell_quartet<C, LA, LB, LC, LD, BOYS, true, true>(t, p, g, s_bra, q, out, bfC, bfD);
+    digest(q, out, scale, bfC, bfD);
   }
-  if (kTwoPass) __syncthreads();  // the queue is complete / pass 1 is done
+  for (; it < nk; it += T) {
+    const int q = s_list[it];
+    double out[C::kOut];
+    int bfC, bfD;
+    const double scale =
+        shell_quartet<C, LA, LB, LC, LD, BOYS, true, false>(t, p, g, s_bra, q, out, bfC, bfD);
+    digest(q, out, scale, bfC, bfD);
   }
 
   // bra block of J: registers -> warp reduce -> one atomic per warp and component
@@ -565,10 +582,158 @@ eri_jk_block_kernel(const EriTask t) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Warp-per-bra-pair J/K kernel for "light" bra pairs (fewer surviving kets than one pass of the
+// block kernel).  One warp owns one bra pair and ALL its kets: it sorts them by regime in its
+// slice of shared memory exactly like the block kernel ([far | grid | corrected]) and walks the
+// list 32 kets at a time, far-field chunks through primitive_quartet_far.  D and K are
+// touched in global memory (scattered 8-byte loads / fp64 atomics), the bra block of J
+// accumulates in registers over the whole ket list.
+// Dynamic shared memory per warp: K2_bra primitive pairs + light_cap ints.
+// ---------------------------------------------------------------------------------------
+template <int LA, int LB, int LC, int LD, int BOYS>
+__global__ void __launch_bounds__(kThreads) eri_jk_light_kernel(const EriTask t) {
+  using C = EriClass<LA, LB, LC, LD>;
+  constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
+  constexpr bool kUnroll = C::kOut <= 81;
+  constexpr int kRegimes = BOYS == kBoysReference ? 3 : 2;
+  extern __shared__ double smem[];
+
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long w = ((long long)blockIdx.x * t.nranks + t.rank) * kWarpsPerBlock + wib;
+  if (w >= t.nlight) return;  // whole warp leaves together
+  const int p = __ldg(t.lp + (int)w);
+  const int nq = __ldg(t.nq + p);
+  const int N = t.N, sb = t.bra.stride, sk = t.ket.stride;
+
+  const size_t per_warp = (size_t)t.bra.K2 * sizeof(PrimPair) + (size_t)t.light_cap * sizeof(int);
+  PrimPair* s_bra = reinterpret_cast<PrimPair*>(reinterpret_cast<char*>(smem) +
+                                                (size_t)wib * ((per_warp + 7) & ~(size_t)7));
+  int* s_list = reinterpret_cast<int*>(s_bra + t.bra.K2);
+  for (int k = lane; k < t.bra.K2; k += 32) s_bra[k] = load_prim(t.bra, k, p);
+  const BraGeom g = load_bra_geom(t.bra, p);
+  const int bfA = __ldg(t.bra.idx + p), bfB = __ldg(t.bra.idx + sb + p);
+
+  // regime sort (warp-local: ballots and running cursors, no atomics)
+  int n_far = 0;
+  {
+    const BraBound bb = load_bra_bound(t.bra, p);
+    const double xcorr = ref_exact_from(C::kL) + 2.0;
+    int n0 = 0, n1 = 0;
+    for (int base = 0; base < nq; base += 32) {
+      const int i = base + lane;
+      const int cls = i < nq ? quartet_regime<kRegimes>(bb, t.ket, i, xcorr, t.far_sched) : 3;
+      n0 += __popc(__ballot_sync(0xffffffffu, cls == 0));
+      n1 += __popc(__ballot_sync(0xffffffffu, cls == 1));
+    }
+    int cur[3] = {0, n0, n0 + n1};
+    for (int base = 0; base < nq; base += 32) {
+      const int i = base + lane;
+      const int cls = i < nq ? quartet_regime<kRegimes>(bb, t.ket, i, xcorr, t.far_sched) : 3;
+#pragma unroll
+      for (int c = 0; c < kRegimes; ++c) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+        if (cls == c) s_list[cur[c] + __popc(m & ((1u << lane) - 1u))] = i;
+        cur[c] += __popc(m);
+      }
+    }
+    n_far = n0;
+  }
+  __syncwarp();
+
+  double Dab[NA * NB], jab[NA * NB];
+#pragma unroll
+  for (int i = 0; i < NA * NB; ++i) {
+    Dab[i] = __ldg(t.bra.Dp + (size_t)i * sb + p);
+    jab[i] = 0.0;
+  }
+  const double* __restrict__ D = t.D;
+
+  auto digest = [&](int q, const double* __restrict__ out, double scale, int bfC, int bfD) {
+    double jcd[NC * ND], kac[NA * NC], kad[NA * ND], kbc[NB * NC], kbd[NB * ND];
+    double Dcd[NC * ND], Dac[NA * NC], Dad[NA * ND], Dbc[NB * NC], Dbd[NB * ND];
+#pragma unroll
+    for (int i = 0; i < NC * ND; ++i) { jcd[i] = 0.0; Dcd[i] = __ldg(t.ket.Dp + (size_t)i * sk + q); }
+#pragma unroll
+    for (int i = 0; i < NA * NC; ++i) {
+      kac[i] = 0.0;
+      Dac[i] = __ldg(D + (size_t)(bfA + i / NC) * N + bfC + i % NC);
+    }
+#pragma unroll
+    for (int i = 0; i < NA * ND; ++i) {
+      kad[i] = 0.0;
+      Dad[i] = __ldg(D + (size_t)(bfA + i / ND) * N + bfD + i % ND);
+    }
+#pragma unroll
+    for (int i = 0; i < NB * NC; ++i) {
+      kbc[i] = 0.0;
+      Dbc[i] = __ldg(D + (size_t)(bfB + i / NC) * N + bfC + i % NC);
+    }
+#pragma unroll
+    for (int i = 0; i < NB * ND; ++i) {
+      kbd[i] = 0.0;
+      Dbd[i] = __ldg(D + (size_t)(bfB + i / ND) * N + bfD + i % ND);
+    }
+#pragma unroll(kUnroll ? C::kOut : 1)
+    for (int o = 0; o < C::kOut; ++o) {
+      const int d = o % ND, c = (o / ND) % NC, b = (o / (ND * NC)) % NB, a = o / (ND * NC * NB);
+      const double v = scale * out[o];
+      const double v2 = v + v;
+      jab[a * NB + b] = fma(v2, Dcd[c * ND + d], jab[a * NB + b]);
+      jcd[c * ND + d] = fma(v2, Dab[a * NB + b], jcd[c * ND + d]);
+      kac[a * NC + c] = fma(v, Dbd[b * ND + d], kac[a * NC + c]);
+      kad[a * ND + d] = fma(v, Dbc[b * NC + c], kad[a * ND + d]);
+      kbc[b * NC + c] = fma(v, Dad[a * ND + d], kbc[b * NC + c]);
+      kbd[b * ND + d] = fma(v, Dac[a * NC + c], kbd[b * ND + d]);
+    }
+#pragma unroll
+    for (int i = 0; i < NC * ND; ++i) atomicAdd(t.ket.Jp + (size_t)i * sk + q, jcd[i]);
+#pragma unroll
+    for (int i = 0; i < NA * NC; ++i)
+      atomicAdd(t.Kh + (size_t)(bfA + i / NC) * N + bfC + i % NC, kac[i]);
+#pragma unroll
+    for (int i = 0; i < NA * ND; ++i)
+      atomicAdd(t.Kh + (size_t)(bfA + i / ND) * N + bfD + i % ND, kad[i]);
+#pragma unroll
+    for (int i = 0; i < NB * NC; ++i)
+      atomicAdd(t.Kh + (size_t)(bfB + i / NC) * N + bfC + i % NC, kbc[i]);
+#pragma unroll
+    for (int i = 0; i < NB * ND; ++i)
+      atomicAdd(t.Kh + (size_t)(bfB + i / ND) * N + bfD + i % ND, kbd[i]);
+  };
+
+  int it = lane;
+  for (; it < n_far; it += 32) {
+    const int q = s_list[it];
+    double out[C::kOut];
+    int bfC, bfD;
+    const double scale =
+        shell_quartet<C, LA, LB, LC, LD, BOYS, true, true>(t, p, g, s_bra, q, out, bfC, bfD);
+    digest(q, out, scale, bfC, bfD);
+  }
+  for (; it < nq; it += 32) {
+    const int q = s_list[it];
+    double out[C::kOut];
+    int bfC, bfD;
+    const double scale =
+        shell_quartet<C, LA, LB, LC, LD, BOYS, true, false>(t, p, g, s_bra, q, out, bfC, bfD);
+    digest(q, out, scale, bfC, bfD);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < NA * NB; ++i) {
+    const double s = warp_sum(jab[i]);
+    if (lane == 0 && s != 0.0) atomicAdd(t.bra.Jp + (size_t)i * sb + p, s);
+  }
+}
+
 // Host-side launcher signatures, one pair per class (eri_class_tu.cu)
 typedef cudaError_t (*EriLaunchFn)(int boys, int mode, const EriTask& task, unsigned grid,
                                    cudaStream_t stream);
 typedef cudaError_t (*EriBlockLaunchFn)(int boys, const EriTask& task, unsigned grid,
+                                        size_t smem_bytes, cudaStream_t stream);
+typedef cudaError_t (*EriLightLaunchFn)(int boys, const EriTask& task, unsigned grid,
                                         size_t smem_bytes, cudaStream_t stream);
 struct EriBlockInfo { int threads; int kets_per_block; };
 

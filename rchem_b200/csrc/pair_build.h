@@ -38,6 +38,7 @@ inline void build_prim_pairs(const Shell& A, const Shell& B, std::vector<PrimPai
       // exp(-aa*ab*rab2/gamma) as in cints.c:113, the 1/gamma of cints.c:112, and the
       // contraction coefficient x norm of both primitives
       pp.pref = A.cn[i] * B.cn[j] * std::exp(-aa * ab * rab2 / pp.zeta) / pp.zeta;
+      pp.pfar = 5.5683279968317078453 * pp.pref / std::sqrt(pp.zeta);  // pi^(3/2)
       out->push_back(pp);
     }
 }
@@ -58,6 +59,35 @@ inline int build_significant_prim_pairs(const Shell& A, const Shell& B, double e
   std::stable_sort(out->begin(), out->end(),
                    [](const PrimPair& x, const PrimPair& y) { return x.zeta < y.zeta; });
   return (int)n;
+}
+
+// Bounding sphere of the primitive-pair centres of a shell pair and its most diffuse exponent
+// sum: every primitive quartet between two shell pairs has
+//   x = rho |P - Q|^2 >= rho(zmin_b, zmin_k) * (|M_b - M_k| - rad_b - rad_k)^2,
+// rho(z, e) = z e/(z + e) being increasing in both arguments.  The block kernel uses it to
+// PROVE a shell quartet far-field (eri_kernel.cuh).
+struct PairBound {
+  double M[3];
+  double rad;
+  double zmin;
+};
+inline PairBound bound_prim_pairs(const std::vector<PrimPair>& pps) {
+  PairBound pb{};
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  pb.zmin = 1e300;
+  for (const PrimPair& pp : pps) {
+    const double P[3] = {pp.Px, pp.Py, pp.Pz};
+    for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], P[d]); hi[d] = std::max(hi[d], P[d]); }
+    pb.zmin = std::min(pb.zmin, pp.zeta);
+  }
+  for (int d = 0; d < 3; ++d) pb.M[d] = 0.5 * (lo[d] + hi[d]);
+  double r2 = 0.0;
+  for (const PrimPair& pp : pps) {
+    const double dx = pp.Px - pb.M[0], dy = pp.Py - pb.M[1], dz = pp.Pz - pb.M[2];
+    r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+  }
+  pb.rad = r2 > 0.0 ? std::sqrt(r2) * (1.0 + 1e-12) + 1e-300 : 0.0;
+  return pb;
 }
 
 // exact Boys tables for boys_exact (eri_core.h): one table per total angular momentum

@@ -71,6 +71,8 @@ def hostcheck():
     H.hostcheck_boys.argtypes = [C.c_int, C.c_int, C.c_double, dp]
     H.hostcheck_boys.restype = None
     H.hostcheck_ref_tables_ok.restype = C.c_int
+    H.hostcheck_last_min_x.restype = C.c_double
+    H.hostcheck_last_proved_far.restype = C.c_int
     return H
 
 

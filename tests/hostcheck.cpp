@@ -37,6 +37,12 @@ namespace rchem {
 #include "../rchem_b200/csrc/gen/eri_class_2221.inc"
 #include "../rchem_b200/csrc/gen/eri_class_2222.inc"
 
+// BOYS == kBoysFarForm (test-only value): every primitive quartet through the far-field form
+// primitive_quartet_far, whatever its x; *min_x reports the smallest Boys argument met and
+// *proved_far what the block kernel's bounding-sphere test (eri_kernel.cuh) says.
+constexpr int kBoysFarForm = 4;
+static double g_min_x = 0.0;
+static int g_proved_far = 0;
 template <class C, int BOYS>
 void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const Shell& Cc,
                    const Shell& D, const BoysTabs& tabs, double* out) {
@@ -44,10 +50,28 @@ void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const She
   build_prim_pairs(A, B, &bra);
   build_prim_pairs(Cc, D, &ket);
   std::vector<double> acc(C::kTargets, 0.0);
+  if (BOYS == kBoysFarForm) {
+    g_min_x = 1e300;
+    for (const PrimPair& k : ket)
+      for (const PrimPair& b : bra) {
+        const double dx = b.Px - k.Px, dy = b.Py - k.Py, dz = b.Pz - k.Pz;
+        g_min_x = std::min(g_min_x, b.zeta * k.zeta / (b.zeta + k.zeta) * (dx * dx + dy * dy + dz * dz));
+      }
+    const PairBound pb = bound_prim_pairs(bra), pk = bound_prim_pairs(ket);
+    const double dx = pb.M[0] - pk.M[0], dy = pb.M[1] - pk.M[1], dz = pb.M[2] - pk.M[2];
+    const double rr = pb.rad + pk.rad, d2c = dx * dx + dy * dy + dz * dz;
+    const double dmin = rr > 0.0 ? std::sqrt(d2c) - rr : 1.0;
+    const double d2 = rr > 0.0 ? dmin * dmin : d2c;
+    g_proved_far = dmin > 0.0 && pb.zmin * pk.zmin * d2 >= (double)kBoysXMax * (pb.zmin + pk.zmin);
+  }
   for (const PrimPair& k : ket)
     for (const PrimPair& b : bra)
-      primitive_quartet<C, BOYS>(b, k, A.ctr[0], A.ctr[1], A.ctr[2], Cc.ctr[0], Cc.ctr[1],
-                                 Cc.ctr[2], tabs, acc.data());
+      if (BOYS == kBoysFarForm)
+        primitive_quartet_far<C>(b, k, A.ctr[0], A.ctr[1], A.ctr[2], Cc.ctr[0], Cc.ctr[1],
+                                 Cc.ctr[2], acc.data());
+      else
+        primitive_quartet<C, BOYS == kBoysFarForm ? kBoysExact : BOYS>(
+            b, k, A.ctr[0], A.ctr[1], A.ctr[2], Cc.ctr[0], Cc.ctr[1], Cc.ctr[2], tabs, acc.data());
   C::hrr(acc.data(), A.ctr[0] - B.ctr[0], A.ctr[1] - B.ctr[1], A.ctr[2] - B.ctr[2],
          Cc.ctr[0] - D.ctr[0], Cc.ctr[1] - D.ctr[1], Cc.ctr[2] - D.ctr[2], out);
   const int na = ncart(A.l), nb = ncart(B.l), nc = ncart(Cc.l), nd = ncart(D.l);
@@ -135,6 +159,9 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
     if (boys == kBoysReference)                                                             \
       shell_quartet<EriClass<la, lb, lc, ld>, kBoysReference>(ss, A, B, C, D,                \
                                                               T.tabs(la + lb + lc + ld), out); \
+    else if (boys == kBoysFarForm)                                                          \
+      shell_quartet<EriClass<la, lb, lc, ld>, kBoysFarForm>(ss, A, B, C, D,                  \
+                                                            T.tabs(la + lb + lc + ld), out); \
     else                                                                                    \
       shell_quartet<EriClass<la, lb, lc, ld>, kBoysExact>(ss, A, B, C, D,                    \
                                                           T.tabs(la + lb + lc + ld), out);  \
@@ -144,6 +171,10 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
 #undef X
   return -2;
 }
+
+// what the last far-form call (boys = 4) saw: smallest Boys argument, bounding-sphere verdict
+extern "C" double hostcheck_last_min_x() { return g_min_x; }
+extern "C" int hostcheck_last_proved_far() { return g_proved_far; }
 
 extern "C" int hostcheck_ref_tables_ok() {
   return all_tabs().delta_ok ? 1 : 0;

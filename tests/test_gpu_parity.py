@@ -453,3 +453,51 @@ def test_prim_eps_option_does_not_change_results(rc, orc, geo):
         out.append((J, K, b.stats()["prim_quartets"]))
     assert out[0][2] < out[1][2]  # primitive pairs were dropped ...
     assert np.abs(out[0][0] - out[1][0]).max() < 1e-13 and np.abs(out[0][1] - out[1][1]).max() < 1e-13
+
+
+# ---- far-field scheduling (primitive_quartet_far through the block and light kernels) -----------
+def test_far_field_pair_of_waters_vs_oracle(rc, orc, geo, ref_or_restated):
+    """Two waters 25 bohr apart, 6-31G*: most inter-molecular quartets are PROVED far-field and
+    go through the point-multipole form; J/K must still match the reference to 1e-12."""
+    z1, x1 = geo.molecule(geo.WATER_CRAWFORD)
+    z = np.concatenate([z1, z1])
+    x = np.concatenate([x1, x1[:, [2, 0, 1]] + np.array([25.0, 3.0, -4.0])])
+    b = rc.Basis.new(z, x, "6-31G*")
+    ob = orc.make_basis(z, x, "6-31G*")
+    n = ob.n
+    D = geo.synthetic_density(n)
+    with ref_or_restated():
+        Jo, Ko = orc.jk_inmem(orc.build_I(ob), D)
+    J, K = np.zeros((n, n)), np.zeros((n, n))
+    rc.JK_direct(J, K, b, D)
+    assert np.abs(J - Jo).max() < TOL and np.abs(K - Ko).max() < TOL
+    b.set_far_sched(False)  # the general code only
+    J0, K0 = np.zeros((n, n)), np.zeros((n, n))
+    rc.JK_direct(J0, K0, b, D)
+    assert np.abs(J0 - Jo).max() < TOL and np.abs(K0 - Ko).max() < TOL
+    assert np.abs(J - J0).max() < 1e-13 and np.abs(K - K0).max() < 1e-13
+
+
+@pytest.mark.parametrize("nw,basis_name,tau", [(27, "6-31G", 0.0), (27, "6-31G", 1e-10),
+                                               (12, "6-31G*", 0.0), (27, "STO-3G", 1e-10)])
+def test_far_scheduling_equals_general_code(rc, geo, nw, basis_name, tau):
+    """Clusters large enough for the block kernel (heavy bra pairs) and the light kernel to
+    sort their kets into [far | grid | corrected]: J/K with the far-field routing must equal
+    J/K with every quartet through the general code (itself checked against the oracle
+    above), in both Boys flavours."""
+    z, x = geo.water_cluster(nw)
+    b = rc.Basis.new(z, x, basis_name)
+    b.set_schwarz_tau(tau)
+    n = b.nbf
+    D = geo.synthetic_density(n)
+    for boys in (rc.BOYS_REFERENCE, rc.BOYS_EXACT):
+        b.set_boys(boys)
+        out = []
+        for far in (True, False):
+            b.set_far_sched(far)
+            J, K = np.zeros((n, n)), np.zeros((n, n))
+            rc.JK_direct(J, K, b, D)
+            out.append((J, K))
+        assert np.abs(out[0][0] - out[1][0]).max() < 1e-12, (boys, np.abs(out[0][0] - out[1][0]).max())
+        assert np.abs(out[0][1] - out[1][1]).max() < 1e-12, (boys, np.abs(out[0][1] - out[1][1]).max())
+        assert np.abs(out[0][0]).max() > 1e-3

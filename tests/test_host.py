@@ -158,6 +158,53 @@ def test_all_21_classes_against_oracle(hostcheck, orc, geo, ref_or_restated):
     assert 1e-9 < np.abs(I_x - I_ref).max() < 2e-8  # the two flavours differ by the Boys error
 
 
+def test_far_field_form_all_21_classes(hostcheck, orc, geo):
+    """primitive_quartet_far (eri_core.h): for shell quartets whose every primitive has
+    x >= 48 the rho-free point-multipole form must equal the general code (exact Boys), which
+    takes its asymptotic branch there; and the bounding-sphere proof the block kernel uses
+    must never call a quartet far that has a primitive with x < 48."""
+    z1, x1 = geo.molecule(geo.WATER_CRAWFORD)
+    rng = np.random.default_rng(7)
+    seen = set()
+    worst = 0.0
+    n_proved = n_far = n_total = 0
+    for shift in ([9.0, 0.0, 0.0], [14.0, 3.0, -2.0], [25.0, -11.0, 7.0], [60.0, 40.0, 10.0]):
+        z = np.concatenate([z1, z1])
+        x = np.concatenate([x1, x1 @ np.linalg.qr(rng.standard_normal((3, 3)))[0] + np.array(shift)])
+        ob = orc.make_basis(z, x, "6-31G*")
+        ls = np.zeros(ob.n, dtype=np.int32)
+        bf = np.zeros(ob.n, dtype=np.int32)
+        ns = hostcheck.hostcheck_nshells(*ob.args(), ls, bf)
+        half = ns // 2
+        far_out, gen_out = np.zeros(1296), np.zeros(1296)
+        quartets = [(sa, sb, sc, sd) for sa in range(half) for sb in range(half)
+                    for sc in range(half, ns) for sd in range(half, ns)
+                    if ls[sa] >= ls[sb] and ls[sc] >= ls[sd] and (ls[sa], ls[sb]) >= (ls[sc], ls[sd])]
+        per_class = {}
+        for i in rng.permutation(len(quartets)):  # up to 60 quartets of every class
+            sa, sb, sc, sd = quartets[i]
+            key = (ls[sa], ls[sb], ls[sc], ls[sd])
+            if per_class.setdefault(key, 0) >= 60:
+                continue
+            per_class[key] += 1
+            n = hostcheck.hostcheck_shell_quartet(*ob.args(), sa, sb, sc, sd, 4, far_out)
+            min_x, proved = hostcheck.hostcheck_last_min_x(), hostcheck.hostcheck_last_proved_far()
+            n_total += 1
+            n_proved += proved
+            assert not (proved and min_x < 48.0), (shift, sa, sb, sc, sd, min_x)
+            if min_x < 48.0:
+                continue
+            n_far += 1
+            assert hostcheck.hostcheck_shell_quartet(*ob.args(), sa, sb, sc, sd, 1, gen_out) == n
+            scale = max(np.abs(gen_out[:n]).max(), 1e-300)
+            worst = max(worst, np.abs(far_out[:n] - gen_out[:n]).max() / scale)
+            assert np.abs(far_out[:n] - gen_out[:n]).max() < 1e-14
+            seen.add((ls[sa], ls[sb], ls[sc], ls[sd]))
+    assert len(seen) == 21, sorted(seen)
+    assert worst < 2e-13, worst       # relative to the largest integral of the block
+    assert n_proved > 0.5 * n_far     # the proof is not vacuous
+
+
 def test_boys_reference_restatement_bitwise_iterations(hostcheck, orc):
     g = golden("fgamma_ref.npz")
     F = np.zeros(9)
