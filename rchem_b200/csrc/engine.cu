@@ -177,6 +177,17 @@ __global__ void finalize_j_kernel(const double* __restrict__ Jp, const int* __re
   }
 }
 
+// max |D| (the K-row fixed-point scale of the block kernel needs it): non-negative doubles
+// order like their bit patterns
+__global__ void absmax_kernel(const double* __restrict__ D, size_t n, unsigned long long* out) {
+  unsigned long long m = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = max(m, (unsigned long long)__double_as_longlong(fabs(D[i])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 __global__ void finalize_k_kernel(const double* __restrict__ Kh, double* __restrict__ K, int N) {
   // K = Kh + Kh^T  (the two transposed halves of the 8-fold digestion)
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,6 +307,8 @@ struct rchem_basis {
   double* d_delta_thr = nullptr; // boys_delta.h tables
   float* d_delta_rows = nullptr;
   double *d_D = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
+  double* d_dmax = nullptr;  // max|D| of the current build (device scalar)
+  double kbound = 0.0;       // 16 max_X sum_Y n_Y Q_XY (EriTask::kbound)
   // maps for tensor_fill_kernel
   int* d_fn_shell = nullptr;
   long long* d_pair_key = nullptr;
@@ -343,6 +356,7 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
     }
     geom[9 * st + s] = pb.rad;
     geom[10 * st + s] = pb.zmin;
+    geom[11 * st + s] = bt.Q.empty() ? 0.0 : Q[s];
     idx[s] = A.bf0;
     idx[st + s] = B.bf0;
     idx[2 * st + s] = (bt.shA[src] == bt.shB[src]) ? 1 : 0;
@@ -480,6 +494,17 @@ int ensure_ready(rchem_basis* h) {
     if (rc) return rc;
   }
 
+  {  // Schwarz row sums for the K-row fixed-point bound (eri_kernel.cuh krow_add)
+    std::vector<double> R(sh.size(), 0.0);
+    for (const Batch& bt : h->batches)
+      for (int p = 0; p < bt.npairs; ++p) {
+        const int a = bt.shA[p], b = bt.shB[p];
+        R[a] += ncart(sh[b].l) * bt.Q[p];
+        if (a != b) R[b] += ncart(sh[a].l) * bt.Q[p];
+      }
+    h->kbound = 16.0 * *std::max_element(R.begin(), R.end());
+  }
+  CUDA_OK(cudaMalloc(&h->d_dmax, sizeof(double)));
   const size_t nn = (size_t)h->N * h->N;
   CUDA_OK(cudaMalloc(&h->d_D, nn * sizeof(double)));
   CUDA_OK(cudaMalloc(&h->d_Kh, nn * sizeof(double)));
@@ -802,7 +827,7 @@ void rchem_basis_destroy(rchem_basis* h) {
     for (Batch& bt : h->batches) {
       cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_idx); cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
     }
-    cudaFree(h->d_boys); cudaFree(h->d_delta_thr); cudaFree(h->d_delta_rows); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK);
+    cudaFree(h->d_boys); cudaFree(h->d_delta_thr); cudaFree(h->d_delta_rows); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK); cudaFree(h->d_dmax);
     cudaFree(h->d_fn_shell); cudaFree(h->d_pair_key); cudaFree(h->d_pair_fwd);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -960,10 +985,14 @@ int rchem_jk_direct_device(rchem_basis* h, const double* D_dev, double* JK_dev, 
         D_dev, N, bt.d_idx, bt.npairs, bt.stride, ncart(bt.lb), bt.ncomp(), bt.d_Dp);
   }
   CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemsetAsync(h->d_dmax, 0, sizeof(double), h->stream));
+  absmax_kernel<<<148, 256, 0, h->stream>>>(D_dev, nn, reinterpret_cast<unsigned long long*>(h->d_dmax));
   EriTask proto;
   fill_common(h, &proto);
   proto.D = D_dev;
   proto.Kh = h->d_Kh;
+  proto.dmax = h->d_dmax;
+  proto.kbound = h->kbound;
   rc = run_tasks(h, kModeJK, proto, rank, nranks);
   if (rc) return rc;
   for (const Batch& bt : h->batches)
@@ -971,7 +1000,7 @@ int rchem_jk_direct_device(rchem_basis* h, const double* D_dev, double* JK_dev, 
         bt.d_Jp, bt.d_idx, bt.npairs, bt.stride, ncart(bt.lb), bt.ncomp(), N, JK_dev);
   finalize_k_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, h->stream>>>(h->d_Kh, JK_dev + nn, N);
   CUDA_OK(cudaGetLastError());
-  h->stats.launches += 2 * (int)h->batches.size() + 1;
+  h->stats.launches += 2 * (int)h->batches.size() + 2;  // pack_d, finalize_j per batch; absmax, finalize_k
   return RCHEM_OK;
 }
 

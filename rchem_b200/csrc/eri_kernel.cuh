@@ -36,10 +36,10 @@ enum EriMode : int { kModeJK = 0, kModeTensor = 1, kModeSchwarz = 2 };
 
 // Device view of one shell-pair batch.  prim holds kPrimFields [K2][stride] arrays in the order
 // zeta, rzeta, Px, Py, Pz, pref, pfar; geom holds kGeomFields [stride] arrays Ax,Ay,Az,
-// ABx,ABy,ABz, then the pair's bounding data Mx,My,Mz,rad,zmin (pair_build.h PairBound);
-// idx holds three [stride] int arrays bfA, bfB, diag.
+// ABx,ABy,ABz, then the pair's bounding data Mx,My,Mz,rad,zmin (pair_build.h PairBound) and its
+// Schwarz bound Q; idx holds three [stride] int arrays bfA, bfB, diag.
 constexpr int kPrimFields = 7;
-constexpr int kGeomFields = 11;
+constexpr int kGeomFields = 12;
 struct BatchView {
   const double* prim;
   const double* geom;
@@ -59,6 +59,8 @@ struct EriTask {
   int same;                      // bra batch == ket batch (then ket q <= p, and p==q is diagonal)
   int rank, nranks;              // multi-GPU: this process takes blocks b with b % nranks == rank
   int far_sched;                 // 1: prove-and-route far-field quartets (0 = tuning/debug)
+  const double* dmax;            // device scalar max|D|                  (block kernel, K rows)
+  double kbound;                 // 16 max_X sum_Y n_Y Q_XY               (block kernel, K rows)
   int N;                         // number of basis functions
   const double* D;               // [N][N] density (symmetric)            kModeJK
   double* Kh;                    // [N][N] half-accumulated K             kModeJK
@@ -353,7 +355,46 @@ template <int LA, int LB, int LC, int LD> struct BlockCfg {
   static constexpr int kKetsPerBlock = kThreadsBlk * RCHEM_BLK_PASSES;
 };
 
-__device__ __forceinline__ void smem_add(double* addr, double v) { atomicAdd(addr, v); }
+// K rows of the block kernel in shared memory.  Shared-memory fp64 (and 64-bit integer)
+// atomicAdd compile to a compare-and-swap loop (LDS + ATOMS.CAST.SPIN, ~9 LSU wavefronts per
+// update; ncu: the LSU data pipe is what bounds the big shallow-contraction launches).  Only
+// 32-bit shared atomics are native, so with RCHEM_K_FIXED the rows are 64-bit FIXED-POINT
+// accumulators split into two 32-bit words: add the low word (the returned old value gives
+// the carry), add high word + carry.  Integer addition commutes, so the 64-bit sum is exact
+// whatever the interleaving -- and the shared-memory part of K becomes order-independent.
+// Scale: a power of two chosen per block from the rigorous bound
+//   sum |terms of one K element| <= 16 Q_ab max|D| max_X sum_Y n_Y Q_XY   (Schwarz),
+// so that the accumulator stays below 2^61: resolution ~2^-61 of that bound (<= 1e-16
+// absolute for the bounds met in practice), far below the 1e-12 parity tolerance.
+#ifndef RCHEM_K_FIXED
+#define RCHEM_K_FIXED 1
+#endif
+__device__ __forceinline__ void krow_add(double* row, int n_row_doubles, int idx, double v,
+                                         double kscale) {
+#if RCHEM_K_FIXED
+  unsigned* lo = reinterpret_cast<unsigned*>(row);
+  unsigned* hi = lo + n_row_doubles;
+  const long long x = __double2ll_rn(v * kscale);
+  const unsigned xl = (unsigned)x;
+  unsigned xh = (unsigned)((unsigned long long)x >> 32);
+  const unsigned old = atomicAdd(lo + idx, xl);
+  xh += (unsigned)((unsigned)(old + xl) < old);  // carry out of the low word
+  if (xh) atomicAdd(hi + idx, xh);
+#else
+  atomicAdd(row + idx, v);
+#endif
+}
+__device__ __forceinline__ double krow_get(const double* row, int n_row_doubles, int idx,
+                                           double kinv) {
+#if RCHEM_K_FIXED
+  const unsigned* lo = reinterpret_cast<const unsigned*>(row);
+  const unsigned* hi = lo + n_row_doubles;
+  const long long acc = (long long)(((unsigned long long)hi[idx] << 32) | lo[idx]);
+  return (double)acc * kinv;
+#else
+  return row[idx];
+#endif
+}
 
 // A shell quartet is scheduled as far-field when the bounding spheres of its two shell pairs
 // prove x >= kFarProvenX for every primitive quartet (boys_exact switches to the asymptotic
@@ -451,6 +492,15 @@ eri_jk_block_kernel(const EriTask t) {
     jab[i] = 0.0;
   }
 
+  // fixed-point scale of the K rows (krow_add): 2^(61 - e), 2^e > bound
+  double kscale = 1.0, kinv = 1.0;
+  if (RCHEM_K_FIXED) {
+    const double bnd = fmax(__ldg(t.bra.geom + 11 * sb + p) * t.kbound * __ldg(t.dmax), 1e-280);
+    const int e = min(61 - (ilogb(bnd) + 1), 900);
+    kscale = scalbn(1.0, e);
+    kinv = scalbn(1.0, -e);
+  }
+
   // Regime scheduling of this block's kets.  89 % of the primitive quartets of a large
   // cluster are far-field (x >= 48: point-multipole form, no Boys table), 8 % need the Boys
   // grid and -- reference flavour -- 3 % the Fgamma truncation correction; but in list
@@ -532,13 +582,13 @@ eri_jk_block_kernel(const EriTask t) {
 #pragma unroll
     for (int i = 0; i < NC * ND; ++i) atomicAdd(t.ket.Jp + (size_t)i * sk + q, jcd[i]);
 #pragma unroll
-    for (int i = 0; i < NA * NC; ++i) smem_add(Krow_a + (i / NC) * N + bfC + i % NC, kac[i]);
+    for (int i = 0; i < NA * NC; ++i) krow_add(Krow_a, NA * N, (i / NC) * N + bfC + i % NC, kac[i], kscale);
 #pragma unroll
-    for (int i = 0; i < NA * ND; ++i) smem_add(Krow_a + (i / ND) * N + bfD + i % ND, kad[i]);
+    for (int i = 0; i < NA * ND; ++i) krow_add(Krow_a, NA * N, (i / ND) * N + bfD + i % ND, kad[i], kscale);
 #pragma unroll
-    for (int i = 0; i < NB * NC; ++i) smem_add(Krow_b + (i / NC) * N + bfC + i % NC, kbc[i]);
+    for (int i = 0; i < NB * NC; ++i) krow_add(Krow_b, NB * N, (i / NC) * N + bfC + i % NC, kbc[i], kscale);
 #pragma unroll
-    for (int i = 0; i < NB * ND; ++i) smem_add(Krow_b + (i / ND) * N + bfD + i % ND, kbd[i]);
+    for (int i = 0; i < NB * ND; ++i) krow_add(Krow_b, NB * N, (i / ND) * N + bfD + i % ND, kbd[i], kscale);
   };
 
   // Every thread walks the sorted list with stride T: far items first (all warps together in
@@ -572,12 +622,12 @@ eri_jk_block_kernel(const EriTask t) {
   // flush the K rows (only touched entries)
   for (int a = 0; a < NA; ++a)
     for (int j = tid; j < N; j += T) {
-      const double v = Krow_a[a * N + j];
+      const double v = krow_get(Krow_a, NA * N, a * N + j, kinv);
       if (v != 0.0) atomicAdd(t.Kh + (size_t)(bfA + a) * N + j, v);
     }
   for (int b = 0; b < NB; ++b)
     for (int j = tid; j < N; j += T) {
-      const double v = Krow_b[b * N + j];
+      const double v = krow_get(Krow_b, NB * N, b * N + j, kinv);
       if (v != 0.0) atomicAdd(t.Kh + (size_t)(bfB + b) * N + j, v);
     }
 }

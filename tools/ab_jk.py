@@ -43,9 +43,9 @@ def main():
     cfgs = []
     if os.path.exists(base) and "*" not in bas:
         cfgs.append(("base", {"RCHEM_B200_LIB": base}))
-    for far in ("0", "1"):
-        for light in ("0", "1"):
-            cfgs.append((f"new far={far} light={light}", {"RCHEM_FAR": far, "RCHEM_LIGHT": light}))
+    combos = os.environ.get("AB_COMBOS", "00,01,10,11").split(",")  # far,light digits
+    for far, light in combos:
+        cfgs.append((f"new far={far} light={light}", {"RCHEM_FAR": far, "RCHEM_LIGHT": light}))
     for tag, env in cfgs:
         e = dict(os.environ); e.update(env)
         p = subprocess.run([sys.executable, "-c", CHILD, nw, bas, tau, tag], env=e, capture_output=True, text=True, timeout=900)
