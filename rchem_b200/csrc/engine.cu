@@ -35,6 +35,10 @@ namespace rchem {
   cudaError_t launch_eri_block_##tag##_b1(const EriTask&, unsigned, size_t, cudaStream_t);  \
   cudaError_t launch_eri_light_##tag##_b0(const EriTask&, unsigned, size_t, cudaStream_t);  \
   cudaError_t launch_eri_light_##tag##_b1(const EriTask&, unsigned, size_t, cudaStream_t);  \
+  cudaError_t launch_eri_light_multi_##tag##_b0(const EriTask*, const int*, int, unsigned,  \
+                                                size_t, cudaStream_t);                      \
+  cudaError_t launch_eri_light_multi_##tag##_b1(const EriTask*, const int*, int, unsigned,  \
+                                                size_t, cudaStream_t);                      \
   EriBlockInfo block_info_##tag();                                                          \
   static cudaError_t launch_eri_##tag(int boys, int mode, const EriTask& t, unsigned g,     \
                                       cudaStream_t s) {                                     \
@@ -50,6 +54,12 @@ namespace rchem {
                                             size_t smem, cudaStream_t s) {                  \
     return boys == kBoysReference ? launch_eri_light_##tag##_b0(t, g, smem, s)              \
                                   : launch_eri_light_##tag##_b1(t, g, smem, s);             \
+  }                                                                                         \
+  static cudaError_t launch_eri_light_multi_##tag(int boys, const EriTask* t, const int* pf, \
+                                                  int n, unsigned g, size_t smem,           \
+                                                  cudaStream_t s) {                         \
+    return boys == kBoysReference ? launch_eri_light_multi_##tag##_b0(t, pf, n, g, smem, s) \
+                                  : launch_eri_light_multi_##tag##_b1(t, pf, n, g, smem, s); \
   }
 RCHEM_ERI_CLASSES(X)
 #undef X
@@ -108,6 +118,13 @@ static EriBlockLaunchFn find_block_launcher(int la, int lb, int lc, int ld, EriB
 static EriLightLaunchFn find_light_launcher(int la, int lb, int lc, int ld) {
 #define X(a, b, c, d, tag) \
   if (la == a && lb == b && lc == c && ld == d) return launch_eri_light_##tag;
+  RCHEM_ERI_CLASSES(X)
+#undef X
+  return nullptr;
+}
+static EriLightMultiLaunchFn find_light_multi_launcher(int la, int lb, int lc, int ld) {
+#define X(a, b, c, d, tag) \
+  if (la == a && lb == b && lc == c && ld == d) return launch_eri_light_multi_##tag;
   RCHEM_ERI_CLASSES(X)
 #undef X
   return nullptr;
@@ -308,6 +325,13 @@ struct rchem_basis {
   float* d_delta_rows = nullptr;
   double *d_D = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
   double* d_dmax = nullptr;  // max|D| of the current build (device scalar)
+  // merged light launches (one per class): task descriptors and block prefixes
+  EriTask* d_light_tasks = nullptr;
+  int* d_light_prefix = nullptr;
+  EriTask* h_light_tasks = nullptr;  // pinned staging
+  int* h_light_prefix = nullptr;
+  cudaEvent_t ev_light = nullptr;
+  size_t light_tasks_cap = 0;
   double kbound = 0.0;       // 16 max_X sum_Y n_Y Q_XY (EriTask::kbound)
   // maps for tensor_fill_kernel
   int* d_fn_shell = nullptr;
@@ -659,6 +683,90 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
   rchem_stats& st = h->stats;
   st = rchem_stats{};
   st.n_tasks = (int)h->tasks.size();
+  const bool split = mode == kModeJK;
+  // the share of this rank is the block-interleaved 1/nranks slice
+  auto my_blocks = [&](long long nblocks) {
+    return nblocks > rank ? (nblocks - rank + nranks - 1) / nranks : 0LL;
+  };
+  auto make_task = [&](const TaskTable& tt) {
+    const Batch &B = h->batches[tt.bra], &K = h->batches[tt.ket];
+    EriTask t = proto;
+    t.bra = B.view();
+    t.ket = K.view();
+    t.boys.exact = h->d_boys + (size_t)(B.la + B.lb + K.la + K.lb) * kBoysTableLen;
+    t.nq = tt.d_nq;
+    t.same = tt.bra == tt.ket;
+    t.rank = rank;
+    t.nranks = nranks;
+    return t;
+  };
+
+  // Light bra pairs (J/K mode): ONE launch per class over all its tasks.  The descriptors go
+  // through a pinned staging buffer into device memory before the streams fork.
+  struct LightGroup { int la, lb, lc, ld; size_t first, prefix_at; int ntasks; size_t smem; long long grid; };
+  std::vector<LightGroup> groups;
+  static const bool kMergeLight = [] {
+    const char* e = std::getenv("RCHEM_LIGHT_MERGE");
+    return e ? atoi(e) != 0 : true;
+  }();
+  if (split && kMergeLight) {
+    std::map<std::tuple<int, int, int, int>, std::vector<const TaskTable*>> by_class;
+    size_t total = 0;
+    for (const TaskTable& tt : h->tasks) {
+      if (tt.nlight <= 0) continue;
+      const Batch &B = h->batches[tt.bra], &K = h->batches[tt.ket];
+      by_class[std::make_tuple(B.la, B.lb, K.la, K.lb)].push_back(&tt);
+      ++total;
+    }
+    if (total > 0) {
+      if (total > h->light_tasks_cap) {
+        if (h->ev_light) CUDA_OK(cudaEventSynchronize(h->ev_light));
+        if (h->d_light_tasks) { cudaFree(h->d_light_tasks); cudaFree(h->d_light_prefix); cudaFreeHost(h->h_light_tasks); cudaFreeHost(h->h_light_prefix); cudaFreeHost(h->h_light_tasks); cudaFreeHost(h->h_light_prefix); }
+        h->light_tasks_cap = total;
+        CUDA_OK(cudaMalloc(&h->d_light_tasks, total * sizeof(EriTask)));
+        CUDA_OK(cudaMalloc(&h->d_light_prefix, (2 * total + 64) * sizeof(int)));
+        CUDA_OK(cudaMallocHost(&h->h_light_tasks, total * sizeof(EriTask)));
+        CUDA_OK(cudaMallocHost(&h->h_light_prefix, (2 * total + 64) * sizeof(int)));
+        if (!h->ev_light) CUDA_OK(cudaEventCreateWithFlags(&h->ev_light, cudaEventDisableTiming));
+      } else {
+        CUDA_OK(cudaEventSynchronize(h->ev_light));  // the previous build's copy has left the buffer
+      }
+      size_t at = 0, pat = 0;
+      for (auto& kv : by_class) {
+        LightGroup g{std::get<0>(kv.first), std::get<1>(kv.first), std::get<2>(kv.first),
+                     std::get<3>(kv.first), at, pat, 0, 0, 0};
+        int* prefix = h->h_light_prefix + pat;
+        long long blocks = 0;
+        for (const TaskTable* tt : kv.second) {
+          EriTask t = make_task(*tt);
+          t.lp = tt->d_lp;
+          t.nlight = tt->nlight;
+          t.light_cap = tt->light_cap;
+          const long long nblocks = ((long long)tt->nlight + kWarpsPerBlock - 1) / kWarpsPerBlock;
+          const long long mine = my_blocks(nblocks);
+          if (mine <= 0) continue;
+          h->h_light_tasks[at + g.ntasks] = t;
+          prefix[g.ntasks] = (int)blocks;
+          blocks += mine;
+          g.ntasks += 1;
+          g.smem = std::max(g.smem, tt->light_smem);
+        }
+        if (blocks > 0x7fffffffLL) return fail(RCHEM_ERR_TOO_LARGE, "light tasks exceed the grid limit");
+        prefix[g.ntasks] = (int)blocks;
+        g.grid = blocks;
+        g.first = at;
+        at += g.ntasks;
+        pat += g.ntasks + 1;
+        if (g.ntasks > 0) groups.push_back(g);
+      }
+      CUDA_OK(cudaMemcpyAsync(h->d_light_tasks, h->h_light_tasks, at * sizeof(EriTask),
+                              cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(cudaMemcpyAsync(h->d_light_prefix, h->h_light_prefix, pat * sizeof(int),
+                              cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(cudaEventRecord(h->ev_light, h->stream));
+    }
+  }
+
   CUDA_OK(cudaEventRecord(h->ev0, h->stream));
   // fork: the auxiliary streams wait for everything queued so far on the main stream
   CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
@@ -669,18 +777,19 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
     next_stream = (next_stream + 1) % h->n_aux;
     return s;
   };
+  const bool merged = !groups.empty();
+  for (const LightGroup& g : groups) {
+    EriLightMultiLaunchFn mfn = find_light_multi_launcher(g.la, g.lb, g.lc, g.ld);
+    if (!mfn) return fail(RCHEM_ERR_UNSUPPORTED_AM, "no kernel for this class");
+    CUDA_OK(mfn(h->boys, h->d_light_tasks + g.first, h->d_light_prefix + g.prefix_at, g.ntasks,
+                (unsigned)g.grid, g.smem, pick_stream()));
+    st.launches += 1;
+  }
   for (const TaskTable& tt : h->tasks) {
     const Batch &B = h->batches[tt.bra], &K = h->batches[tt.ket];
     st.shell_quartets_all += tt.nquartets_all;
     if (tt.nwarps == 0) continue;
-    EriTask t = proto;
-    t.bra = B.view();
-    t.ket = K.view();
-    t.boys.exact = h->d_boys + (size_t)(B.la + B.lb + K.la + K.lb) * kBoysTableLen;
-    t.nq = tt.d_nq;
-    t.same = tt.bra == tt.ket;
-    t.rank = rank;
-    t.nranks = nranks;
+    EriTask t = make_task(tt);
     EriLaunchFn fn = find_launcher(B.la, B.lb, K.la, K.lb);
     if (!fn) return fail(RCHEM_ERR_UNSUPPORTED_AM, "no kernel for this class");
     const FlopModel* fm = flop_model(B.la, B.lb, K.la, K.lb);
@@ -692,24 +801,20 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
       st.integrals += q * (long long)(ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb));
       if (fm) st.model_flops += q * (k4 * fm->P + fm->H);
     };
-    // the share of this rank is the block-interleaved 1/nranks slice
-    auto my_blocks = [&](long long nblocks) {
-      return nblocks > rank ? (nblocks - rank + nranks - 1) / nranks : 0LL;
-    };
-    const bool split = mode == kModeJK;
-    // --- warp kernel (everything in tensor mode; the light bra pairs in J/K mode) ---
+    // --- warp kernels (everything in tensor mode; the light bra pairs in J/K mode) ---
     const long long nwarps = split ? tt.nwarps_light : tt.nwarps;
     if (split && tt.nlight > 0) {
       // --- warp-per-bra-pair kernel (light bra pairs, J/K mode) ---
-      EriLightLaunchFn lfn = find_light_launcher(B.la, B.lb, K.la, K.lb);
-      t.nq = tt.d_nq;
-      t.lp = tt.d_lp;
-      t.nlight = tt.nlight;
-      t.light_cap = tt.light_cap;
       const long long nblocks = ((long long)tt.nlight + kWarpsPerBlock - 1) / kWarpsPerBlock;
       const long long mine = my_blocks(nblocks);
-      CUDA_OK(lfn(h->boys, t, (unsigned)mine, tt.light_smem, pick_stream()));
-      if (mine > 0) st.launches += 1;
+      if (!merged) {
+        EriLightLaunchFn lfn = find_light_launcher(B.la, B.lb, K.la, K.lb);
+        t.lp = tt.d_lp;
+        t.nlight = tt.nlight;
+        t.light_cap = tt.light_cap;
+        CUDA_OK(lfn(h->boys, t, (unsigned)mine, tt.light_smem, pick_stream()));
+        if (mine > 0) st.launches += 1;
+      }
       account(tt.nquartets_light * (double)mine / (double)nblocks);
     } else if (nwarps > 0) {
       t.warp_prefix = split ? tt.d_prefix_light : tt.d_prefix;
@@ -827,7 +932,7 @@ void rchem_basis_destroy(rchem_basis* h) {
     for (Batch& bt : h->batches) {
       cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_idx); cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
     }
-    cudaFree(h->d_boys); cudaFree(h->d_delta_thr); cudaFree(h->d_delta_rows); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK); cudaFree(h->d_dmax);
+    cudaFree(h->d_boys); cudaFree(h->d_delta_thr); cudaFree(h->d_delta_rows); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK); cudaFree(h->d_dmax); cudaFree(h->d_light_tasks); cudaFree(h->d_light_prefix); cudaFreeHost(h->h_light_tasks); cudaFreeHost(h->h_light_prefix);
     cudaFree(h->d_fn_shell); cudaFree(h->d_pair_key); cudaFree(h->d_pair_fwd);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

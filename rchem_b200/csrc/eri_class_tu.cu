@@ -73,6 +73,21 @@ cudaError_t RCHEM_CAT(launch_eri_light_, RCHEM_SUFFIX)(const EriTask& task, unsi
   }
 }
 
+cudaError_t RCHEM_CAT(launch_eri_light_multi_, RCHEM_SUFFIX)(const EriTask* tasks,
+                                                             const int* blk_prefix, int ntasks,
+                                                             unsigned grid, size_t smem,
+                                                             cudaStream_t stream) {
+  if (grid == 0) return cudaSuccess;
+  if constexpr (kHasBlockKernel) {
+    if (smem > 40 * 1024) return cudaErrorInvalidValue;  // (the engine keeps it below)
+    eri_jk_light_multi_kernel<RCHEM_LA, RCHEM_LB, RCHEM_LC, RCHEM_LD, RCHEM_BOYS>
+        <<<grid, kThreads, smem, stream>>>(tasks, blk_prefix, ntasks);
+    return cudaGetLastError();
+  } else {
+    return cudaErrorNotSupported;
+  }
+}
+
 #if RCHEM_BOYS == 0
 EriBlockInfo RCHEM_CAT(block_info_, RCHEM_TAG)() {
   using Cfg = BlockCfg<RCHEM_LA, RCHEM_LB, RCHEM_LC, RCHEM_LD>;

@@ -41,7 +41,7 @@ def main():
     nw, bas, tau = (sys.argv[1:4] + ["96", "6-31G", "1e-10"][len(sys.argv) - 1:])[:3]
     base = os.path.join(ROOT, "rchem_b200", "librchem_b200_base.so")
     cfgs = []
-    if os.path.exists(base) and "*" not in bas:
+    if os.path.exists(base) and "*" not in bas and not os.environ.get("AB_NOBASE"):
         cfgs.append(("base", {"RCHEM_B200_LIB": base}))
     combos = os.environ.get("AB_COMBOS", "00,01,10,11").split(",")  # far,light digits
     for far, light in combos:
