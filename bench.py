@@ -409,12 +409,12 @@ def run_ours(args):
         "bound": "fp64", "achieved": achieved, "peak": peak_avg, "unit": "TFLOP/s",
         "frac": achieved / peak_avg,
         # DRAM bytes of one step (all ERI launches), from the committed ncu launch list
-        # profiles/r01_launch_summary_h2o96_631g_ref.txt (headline workload, 1 GPU); null for
-        # other workloads / GPU counts
-        "traffic": 4.14e9 if (args.workload == DEFAULT_WORKLOAD and world == 1) else None,
+        # profiles/r01_launch_summary_h2o96_631g_ref_final.txt (headline workload, 1 GPU,
+        # reference Boys); null for other workloads / GPU counts
+        "traffic": 1.43e9 if (args.workload == DEFAULT_WORKLOAD and world == 1) else None,
         "peak_source": "measured in this run: DFMA microbenchmark rchem_fp64_peak (avg of 10; "
                        f"best {peak_best:.2f}); MEASURED_PEAKS.json has no FP64 entry",
-        "kernel": "eri_jk_block_kernel<la,lb,lc,ld,boys> + eri_kernel<..,JK> (all class "
+        "kernel": "eri_jk_block_kernel<la,lb,lc,ld,boys> + eri_jk_light_multi_kernel<..> (all class "
                   "instantiations of one step; the (ps|ss) block kernel is the largest share)",
         "kernel_ms_per_step": k_ms,
         "algorithmic_flops_per_step": flops,

@@ -615,10 +615,12 @@ int ensure_tasks(rchem_basis* h) {
                       (size_t)B.K2 * sizeof(PrimPair) + (size_t)info.kets_per_block * sizeof(int) + 64;
       const bool rows_fit = tt.smem_bytes <= kMaxBlockSmem && info.threads > 0;
       // a bra pair is "heavy" when its ket prefix fills the block kernel's threads at least
-      // kHeavyPasses times (the last, partial pass of a block idles most of its warps)
-      static const double kHeavyPasses = [] {  // tuning knob; 1 pass measured best (0.125..8)
+      // kHeavyPasses times; below that the warp-per-bra-pair kernel (no D/K row staging, no
+      // block-wide barriers) is the faster home
+      static const double kHeavyPasses = [] {  // tuning knob; measured on (H2O)96/6-31G with
+        // the light kernel: 0.25: 176 ms, 0.5: 151, 1: 138, 1.5: 135, 2: 135, 3: 136, 4: 146
         const char* e = std::getenv("RCHEM_HEAVY_PASSES");
-        return e ? std::max(0.01, atof(e)) : 1.0;
+        return e ? std::max(0.01, atof(e)) : 2.0;
       }();
       std::vector<int> nq_light(B.npairs), hp;
       std::vector<long long> prefix_light(B.npairs + 1, 0), hblk(1, 0);
