@@ -11,14 +11,19 @@
 //     quartets, accumulating the [e0|f0] VRR targets in registers, then HRR, then digests the
 //     block into J/K (8-fold symmetry, 6 updates per integral), writes the canonical tensor
 //     element, or reduces it to a Schwarz bound;
-//   * eri_kernel (warp kernel): one WARP per (bra pair p, 32 consecutive kets) -- bra data
+//   * eri_kernel (chunk kernel): one WARP per (bra pair p, 32 consecutive kets) -- bra data
 //     warp-uniform, ket data coalesced from [primitive][pair] SoA arrays.  Used for the dense
-//     tensor, the Schwarz bounds and the J/K of "light" bra pairs;
+//     tensor, the Schwarz bounds and (fallback) the J/K of bra pairs no other kernel takes;
 //   * eri_jk_block_kernel: one BLOCK per (bra pair, <= 8 T kets) for "heavy" bra pairs, with the
-//     bra pair's D rows and K accumulators in shared memory, and (reference Boys flavour)
-//     either a regime-sorted ket order or a dense second pass for quartets that need the
-//     Fgamma truncation correction.
-// All arithmetic is IEEE fp64 on the FP64 pipe.
+//     bra pair's D rows and K accumulators in shared memory (K as 64-bit fixed point on native
+//     32-bit shared atomics);
+//   * eri_jk_light_kernel / eri_jk_light_multi_kernel: one WARP per "light" bra pair and all
+//     its kets, every light task of a class merged into one launch;
+//   * both J/K kernels sort their kets by regime -- PROVED far-field / Boys grid / grid +
+//     Fgamma correction -- and run the far-field ones through the rho-free point-multipole
+//     form primitive_quartet_far (eri_core.h): no Boys table, no 1/sqrt(zeta+eta).
+// All integral arithmetic is IEEE fp64 on the FP64 pipe; only the shared-memory K accumulators
+// of the block kernel are 64-bit fixed point (krow_add), converted back to fp64 at the flush.
 //
 // Reference: the loops this replaces are basis.rs:383-428 (JK_direct) and basis.rs:430-460
 // (build_I); the per-primitive arithmetic is chgp.c:113-135,412-586 / cints.c:72-115.
@@ -505,7 +510,8 @@ eri_jk_block_kernel(const EriTask t) {
   // cluster are far-field (x >= 48: point-multipole form, no Boys table), 8 % need the Boys
   // grid and -- reference flavour -- 3 % the Fgamma truncation correction; but in list
   // (Schwarz) order nearly every warp holds a lane of each regime and pays for all three.
-  // The block therefore sorts its kets in shared memory into [far | grid | corrected]:
+  // The block therefore sorts its kets in shared memory into [far | grid | corrected]
+  // (bra pair fixed, so one pass over the kets' bounding data decides):
   //   * far: PROVED from the pairs' bounding data (centre M, radius rad, most diffuse
   //     exponent zmin): rho(zmin_b, zmin_k) (|M_b - M_k| - rad_b - rad_k)^2 >= 48 bounds every
   //     primitive quartet's x from below.  These run the far-only code (primitive_quartet_far);
