@@ -783,8 +783,19 @@ __device__ __forceinline__ void jk_light_body(const EriTask& t, long long blk, d
   }
 }
 
+// Resident blocks per SM the light kernels are compiled for (register cap 65536/(128 n)):
+// the kernel waits on scattered global D loads, so occupancy is worth some spills
+// (measured on the headline workload: 1 -> 134.7 ms, 5 -> 133.7, 6 -> 133.5, 8 -> 136.0).
+#ifndef RCHEM_LIGHT_MINB
+#define RCHEM_LIGHT_MINB 6
+#endif
+template <int LA, int LB, int LC, int LD> struct LightCfg {
+  static constexpr int kMinBlocks =
+      EriClass<LA, LB, LC, LD>::kTargets <= 9 ? RCHEM_LIGHT_MINB : 1;
+};
 template <int LA, int LB, int LC, int LD, int BOYS>
-__global__ void __launch_bounds__(kThreads) eri_jk_light_kernel(const EriTask t) {
+__global__ void __launch_bounds__(kThreads, LightCfg<LA, LB, LC, LD>::kMinBlocks)
+eri_jk_light_kernel(const EriTask t) {
   extern __shared__ double smem[];
   jk_light_body<LA, LB, LC, LD, BOYS>(t, (long long)blockIdx.x * t.nranks + t.rank, smem);
 }
@@ -794,7 +805,7 @@ __global__ void __launch_bounds__(kThreads) eri_jk_light_kernel(const EriTask t)
 // tasks[] lives in device memory; block b belongs to task ti with
 // blk_prefix[ti] <= b < blk_prefix[ti + 1] and copies its descriptor into shared memory.
 template <int LA, int LB, int LC, int LD, int BOYS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, LightCfg<LA, LB, LC, LD>::kMinBlocks)
 eri_jk_light_multi_kernel(const EriTask* __restrict__ tasks, const int* __restrict__ blk_prefix,
                           int ntasks) {
   extern __shared__ double smem[];
