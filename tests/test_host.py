@@ -113,6 +113,11 @@ def test_argument_validation(rc, geo):
         b.set_boys(3)
     with pytest.raises(rc.RchemError):
         b.set_schwarz_tau(-1.0)
+    assert rc._lib.rchem_get_option(b._h, rc.OPT_FAR_SCHED) == 1.0  # far-field scheduling: on
+    b.set_far_sched(False)
+    assert rc._lib.rchem_get_option(b._h, rc.OPT_FAR_SCHED) == 0.0
+    with pytest.raises(rc.RchemError):
+        rc._check(rc._lib.rchem_set_option(b._h, rc.OPT_FAR_SCHED, 2.0))
     with pytest.raises(rc.RchemError) as ei:  # g function: tier-1 kernel stops at f
         rc.coulomb_repulsion_batch(np.zeros((1, 12)), np.ones((1, 4)),
                                    np.array([[4, 0, 0] + [0] * 9]), np.ones((1, 4)))
