@@ -353,3 +353,67 @@ def test_bse_json_ingestion(rc, geo):
              "coefficients": [["1.0"]]}]}}}, [8], [[0, 0, 0]])
     with pytest.raises(KeyError):
         bse.basis_from_bse(custom, [1], [[0, 0, 0]])
+
+
+def test_k_row_fixed_point_bound_is_rigorous(hostcheck, orc, geo):
+    """The block kernel accumulates its shared-memory K rows in 64-bit fixed point scaled from
+    the bound  sum |terms of one K element| <= 16 Q_ab max|D| max_X sum_Y n_Y Q_XY
+    (eri_kernel.cuh krow_add, engine.cu kbound).  Check the inequality -- without the safety
+    factor 16 it must already hold with the factor n_B of the bra's second shell -- on every
+    (bra shell pair, bra function, ket function) of water / 6-31G* with oracle integrals."""
+    z, x = geo.molecule(geo.WATER_CRAWFORD)
+    ob = orc.make_basis(z, x, "6-31G*")
+    n = ob.n
+    I = np.abs(orc.build_I(ob, orc.BOYS_EXACT))
+    ls = np.zeros(n, dtype=np.int32)
+    bf = np.zeros(n, dtype=np.int32)
+    ns = hostcheck.hostcheck_nshells(*ob.args(), ls, bf)
+    ls, bf = ls[:ns], bf[:ns]
+    nc = (ls + 1) * (ls + 2) // 2
+    sh_of = np.repeat(np.arange(ns), nc)
+    qf = np.sqrt(np.einsum("ijij->ij", I))                      # per function pair
+    Q = np.zeros((ns, ns))
+    for s in range(ns):
+        for t in range(ns):
+            Q[s, t] = qf[np.ix_(sh_of == s, sh_of == t)].max()  # shell-pair Schwarz bound
+    assert (I <= np.einsum("ij,kl->ijkl", qf, qf) * (1 + 1e-10) + 1e-15).all()  # Cauchy-Schwarz
+    Rmax = (Q * nc[None, :]).sum(axis=1).max()
+    D = np.abs(geo.synthetic_density(n) * 50.0)
+    Dmax = D.max()
+    worst = 0.0
+    for A in range(ns):
+        for B in range(ns):
+            fa, fb = np.where(sh_of == A)[0], np.where(sh_of == B)[0]
+            # K[a, x] receives sum_{b in B} sum_l (ab|xl) D[b,l] from bra pair (A,B), all kets
+            lhs = np.einsum("abxl,bl->ax", I[np.ix_(fa, fb, np.arange(n), np.arange(n))], D[fb, :])
+            bound = Q[A, B] * Dmax * Rmax * len(fb)
+            worst = max(worst, lhs.max() / max(bound, 1e-300))
+            assert lhs.max() <= bound * (1 + 1e-9) + 1e-14, (A, B, lhs.max(), bound)
+    assert 1e-4 < worst <= 1.0  # the bound is neither violated nor absurdly loose
+
+
+def test_split_word_fixed_point_accumulation_is_exact():
+    """krow_add (eri_kernel.cuh) adds a signed 64-bit fixed-point value as two 32-bit atomics:
+    low word first (the returned old value gives the carry), then high word + carry.  Restated
+    here word for word: whatever the order of the additions, (hi, lo) is the exact 64-bit sum,
+    and converting back with the inverse scale recovers the fp64 sum to the resolution."""
+    M32, M64 = 1 << 32, 1 << 64
+    rng = np.random.default_rng(3)
+    for trial in range(50):
+        bound = 10.0 ** rng.uniform(-6, 4)
+        e = min(61 - (int(np.floor(np.log2(bound))) + 1), 900)   # scale 2^e, bound < 2^(61-e)
+        vals = rng.standard_normal(400) * bound / 400.0 * rng.choice([1.0, 1e-6, 1e-12], 400)
+        xs = [int(np.rint(v * 2.0 ** e)) for v in vals]
+        for order in (np.arange(400), rng.permutation(400)):
+            lo = hi = 0
+            for i in order:
+                xu = xs[i] % M64
+                xl, xh = xu % M32, xu >> 32
+                old, lo = lo, (lo + xl) % M32
+                xh = (xh + (1 if (old + xl) % M32 < old else 0)) % M32
+                if xh:
+                    hi = (hi + xh) % M32
+            acc = (hi << 32) | lo
+            acc -= M64 if acc >= 1 << 63 else 0
+            assert acc == sum(xs)
+            assert abs(acc * 2.0 ** -e - vals.sum()) <= 400 * 2.0 ** -(e + 1) + 1e-18 * bound
