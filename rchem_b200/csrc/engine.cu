@@ -939,6 +939,7 @@ void rchem_basis_destroy(rchem_basis* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_light) cudaEventDestroy(h->ev_light);
     for (int i = 0; i < rchem_basis::kAuxStreams; ++i) {
       if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
       if (h->aux[i]) cudaStreamDestroy(h->aux[i]);

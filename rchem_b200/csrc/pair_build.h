@@ -90,6 +90,73 @@ inline PairBound bound_prim_pairs(const std::vector<PrimPair>& pps) {
   return pb;
 }
 
+// Moment-matched compression of a SAME-CENTRE shell pair's primitives for the far-field form
+// (groundwork for round 2; not yet used by the engine).  With rho = 1 (primitive_quartet_far)
+// a primitive enters the [e0|f0] targets only through pfar and powers 0..L of 1/zeta, L the
+// pair's total angular momentum (each power of 1/zeta comes with one unit of angular momentum
+// in the Obara-Saika relations), and all its primitives share P.  For K2 > L+1 any n = L+1
+// pseudo-primitives (w_j, u_j) with  sum_j w_j u_j^i = sum_k pfar_k zeta_k^-i  (i = 0..n-1)
+// therefore give the same contracted targets: a 36-primitive (ss| pair becomes ONE.
+// Nodes: spread over the range of 1/zeta; weights from the Vandermonde system (long double).
+// Returns false when the pair is not same-centre (the centres P differ).
+inline bool compress_far_prim_pairs(const std::vector<PrimPair>& pps, int L,
+                                    std::vector<PrimPair>* out) {
+  out->clear();
+  if (pps.empty()) return false;
+  for (const PrimPair& pp : pps) {  // (alpha A + beta A)/(alpha + beta) may be an ulp off A
+    const double tol = 1e-13 * (1.0 + std::fabs(pps[0].Px) + std::fabs(pps[0].Py) + std::fabs(pps[0].Pz));
+    if (std::fabs(pp.Px - pps[0].Px) > tol || std::fabs(pp.Py - pps[0].Py) > tol ||
+        std::fabs(pp.Pz - pps[0].Pz) > tol)
+      return false;
+  }
+  if ((int)pps.size() <= L + 1) {  // nothing to gain: keep the primitives themselves
+    *out = pps;
+    return true;
+  }
+  const int n = L + 1;
+  std::vector<long double> u(pps.size());
+  for (size_t k = 0; k < pps.size(); ++k) u[k] = 1.0L / (long double)pps[k].zeta;
+  std::vector<long double> sorted = u;
+  std::sort(sorted.begin(), sorted.end());
+  std::vector<long double> node(n), M(n, 0.0L), w(n, 0.0L);
+  for (int j = 0; j < n; ++j) {
+    // Chebyshev-like spread over [min, max] of 1/zeta (distinct for n <= number of distinct values)
+    const long double t = n == 1 ? 0.5L : 0.5L * (1.0L - cosl(3.14159265358979323846L * (j + 0.5L) / n));
+    node[j] = sorted.front() + t * (sorted.back() - sorted.front());
+  }
+  if (n == 1) node[0] = 0.5L * (sorted.front() + sorted.back());
+  for (size_t k = 0; k < pps.size(); ++k) {
+    long double p = (long double)pps[k].pfar;
+    for (int i = 0; i < n; ++i) { M[i] += p; p *= u[k]; }
+  }
+  // solve sum_j w_j node_j^i = M_i by Gaussian elimination on the Vandermonde matrix
+  std::vector<std::vector<long double>> Amat(n, std::vector<long double>(n + 1));
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) Amat[i][j] = powl(node[j], i);
+    Amat[i][n] = M[i];
+  }
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r) if (fabsl(Amat[r][c]) > fabsl(Amat[piv][c])) piv = r;
+    std::swap(Amat[c], Amat[piv]);
+    if (Amat[c][c] == 0.0L) return false;
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      const long double f = Amat[r][c] / Amat[c][c];
+      for (int k = c; k <= n; ++k) Amat[r][k] -= f * Amat[c][k];
+    }
+  }
+  for (int j = 0; j < n; ++j) {
+    PrimPair q = pps[0];
+    q.rzeta = (double)node[j];
+    q.zeta = (double)(1.0L / node[j]);
+    q.pfar = (double)(Amat[j][n] / Amat[j][j]);
+    q.pref = 0.0;  // (the far-field form does not use it)
+    out->push_back(q);
+  }
+  return true;
+}
+
 // exact Boys tables for boys_exact (eri_core.h): one table per total angular momentum
 // L = 0..kBoysMaxL, rows x_i = i/kBoysPerUnit, row = {F_{L+k}(x_i)/k! (k=0..7), exp(-x_i), 0}.
 inline void build_boys_tables(std::vector<double>* tables) {

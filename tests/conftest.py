@@ -73,6 +73,7 @@ def hostcheck():
     H.hostcheck_ref_tables_ok.restype = C.c_int
     H.hostcheck_last_min_x.restype = C.c_double
     H.hostcheck_last_proved_far.restype = C.c_int
+    H.hostcheck_last_prims_used.restype = C.c_int
     return H
 
 

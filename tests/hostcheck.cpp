@@ -41,6 +41,11 @@ namespace rchem {
 // primitive_quartet_far, whatever its x; *min_x reports the smallest Boys argument met and
 // *proved_far what the block kernel's bounding-sphere test (eri_kernel.cuh) says.
 constexpr int kBoysFarForm = 4;
+// BOYS == kBoysFarCompressed (test-only value): the far-field form with the primitives of
+// same-centre shell pairs replaced by their moment-matched pseudo-primitives
+// (compress_far_prim_pairs, pair_build.h).
+constexpr int kBoysFarCompressed = 6;
+static int g_prims_used = 0;
 static double g_min_x = 0.0;
 static int g_proved_far = 0;
 template <class C, int BOYS>
@@ -50,6 +55,12 @@ void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const She
   build_prim_pairs(A, B, &bra);
   build_prim_pairs(Cc, D, &ket);
   std::vector<double> acc(C::kTargets, 0.0);
+  if (BOYS == kBoysFarCompressed) {
+    std::vector<PrimPair> cb, ck;
+    if (compress_far_prim_pairs(bra, A.l + B.l, &cb)) bra.swap(cb);
+    if (compress_far_prim_pairs(ket, Cc.l + D.l, &ck)) ket.swap(ck);
+    g_prims_used = (int)(bra.size() * ket.size());
+  }
   if (BOYS == kBoysFarForm) {
     g_min_x = 1e300;
     for (const PrimPair& k : ket)
@@ -66,11 +77,11 @@ void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const She
   }
   for (const PrimPair& k : ket)
     for (const PrimPair& b : bra)
-      if (BOYS == kBoysFarForm)
+      if (BOYS == kBoysFarForm || BOYS == kBoysFarCompressed)
         primitive_quartet_far<C>(b, k, A.ctr[0], A.ctr[1], A.ctr[2], Cc.ctr[0], Cc.ctr[1],
                                  Cc.ctr[2], acc.data());
       else
-        primitive_quartet<C, BOYS == kBoysFarForm ? kBoysExact : BOYS>(
+        primitive_quartet<C, (BOYS == kBoysFarForm || BOYS == kBoysFarCompressed) ? kBoysExact : BOYS>(
             b, k, A.ctr[0], A.ctr[1], A.ctr[2], Cc.ctr[0], Cc.ctr[1], Cc.ctr[2], tabs, acc.data());
   C::hrr(acc.data(), A.ctr[0] - B.ctr[0], A.ctr[1] - B.ctr[1], A.ctr[2] - B.ctr[2],
          Cc.ctr[0] - D.ctr[0], Cc.ctr[1] - D.ctr[1], Cc.ctr[2] - D.ctr[2], out);
@@ -162,6 +173,9 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
     else if (boys == kBoysFarForm)                                                          \
       shell_quartet<EriClass<la, lb, lc, ld>, kBoysFarForm>(ss, A, B, C, D,                  \
                                                             T.tabs(la + lb + lc + ld), out); \
+    else if (boys == kBoysFarCompressed)                                                    \
+      shell_quartet<EriClass<la, lb, lc, ld>, kBoysFarCompressed>(ss, A, B, C, D,            \
+                                                                  T.tabs(la + lb + lc + ld), out); \
     else                                                                                    \
       shell_quartet<EriClass<la, lb, lc, ld>, kBoysExact>(ss, A, B, C, D,                    \
                                                           T.tabs(la + lb + lc + ld), out);  \
@@ -173,6 +187,7 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
 }
 
 // what the last far-form call (boys = 4) saw: smallest Boys argument, bounding-sphere verdict
+extern "C" int hostcheck_last_prims_used() { return g_prims_used; }
 extern "C" double hostcheck_last_min_x() { return g_min_x; }
 extern "C" int hostcheck_last_proved_far() { return g_proved_far; }
 

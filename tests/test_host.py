@@ -210,6 +210,46 @@ def test_far_field_form_all_21_classes(hostcheck, orc, geo):
     assert n_proved > 0.5 * n_far     # the proof is not vacuous
 
 
+def test_far_field_moment_matched_compression(hostcheck, orc, geo):
+    """Groundwork for round 2 (pair_build.h compress_far_prim_pairs): in the far-field form a
+    same-centre shell pair's primitives enter only through sum_k pfar_k zeta_k^-i, i <= L, so
+    L+1 moment-matched pseudo-primitives reproduce the contracted targets of all K2 primitives
+    -- a 36 x 36 (1s1s|1s1s) contraction becomes 1 x 1.  Checked against the uncompressed
+    far-field form for every same-centre class combination of two distant 6-31G* waters."""
+    z1, x1 = geo.molecule(geo.WATER_CRAWFORD)
+    z = np.concatenate([z1, z1])
+    x = np.concatenate([x1, x1[:, [1, 2, 0]] + np.array([31.0, -7.0, 12.0])])
+    ob = orc.make_basis(z, x, "6-31G*")
+    ls = np.zeros(ob.n, dtype=np.int32)
+    bf = np.zeros(ob.n, dtype=np.int32)
+    ns = hostcheck.hostcheck_nshells(*ob.args(), ls, bf)
+    half = ns // 2
+    org, _, _, _, _, _ = ob.export() if hasattr(ob, "export") else (None,) * 6
+    full, comp = np.zeros(1296), np.zeros(1296)
+    seen, saved, worst = set(), [], 0.0
+    o_shells = [s for s in range(half) if ls[s] >= 0][:6]          # the O atom's shells come first
+    o2_shells = [s + half for s in o_shells]
+    for sa in o_shells:
+        for sb in o_shells:
+            for sc in o2_shells:
+                for sd in o2_shells:
+                    if ls[sa] < ls[sb] or ls[sc] < ls[sd] or (ls[sa], ls[sb]) < (ls[sc], ls[sd]):
+                        continue
+                    n = hostcheck.hostcheck_shell_quartet(*ob.args(), sa, sb, sc, sd, 4, full)
+                    if hostcheck.hostcheck_last_min_x() < 48.0:
+                        continue
+                    assert hostcheck.hostcheck_shell_quartet(*ob.args(), sa, sb, sc, sd, 6, comp) == n
+                    used = hostcheck.hostcheck_last_prims_used()
+                    scale = max(np.abs(full[:n]).max(), 1e-300)
+                    worst = max(worst, np.abs(comp[:n] - full[:n]).max() / scale)
+                    seen.add((ls[sa], ls[sb], ls[sc], ls[sd]))
+                    saved.append(used)
+                    L_bra, L_ket = ls[sa] + ls[sb], ls[sc] + ls[sd]
+                    assert used <= (L_bra + 1) * (L_ket + 1)
+    assert len(seen) == 21, sorted(seen)
+    assert worst < 1e-11, worst
+
+
 def test_boys_reference_restatement_bitwise_iterations(hostcheck, orc):
     g = golden("fgamma_ref.npz")
     F = np.zeros(9)
