@@ -137,12 +137,21 @@ struct Batch {
   std::vector<int> shA, shB;
   std::vector<double> Q;
   double* d_prim = nullptr;
+  double* d_prim_far = nullptr;  // RCHEM_FAR_COMPRESS: compressed far-field primitives
+  int K2far = 0;
+  int same_centre = 0;           // RCHEM_FAR_COMPRESS: batch key (every pair same-centre or none)
   double* d_geom = nullptr;
   int* d_idx = nullptr;
   double* d_Dp = nullptr;  // [ncart(la)*ncart(lb)][stride] packed D blocks
   double* d_Jp = nullptr;  // [ncart(la)*ncart(lb)][stride] packed J blocks
   int ncomp() const { return ncart(la) * ncart(lb); }
-  BatchView view() const { return BatchView{d_prim, d_geom, d_idx, d_Dp, d_Jp, npairs, stride, K2}; }
+  BatchView view() const {
+#if RCHEM_FAR_COMPRESS
+    return BatchView{d_prim, d_geom, d_idx, d_Dp, d_Jp, npairs, stride, K2, d_prim_far, K2far};
+#else
+    return BatchView{d_prim, d_geom, d_idx, d_Dp, d_Jp, npairs, stride, K2};
+#endif
+  }
 };
 
 struct TaskTable {
@@ -355,6 +364,12 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   bt.stride = (np + 31) / 32 * 32;
   const size_t st = bt.stride;
   std::vector<double> prim(kPrimFields * (size_t)bt.K2 * st, 0.0), geom(kGeomFields * st, 0.0);
+#if RCHEM_FAR_COMPRESS
+  // far-field table: same-centre batches hold min(K2, L+1) moment-matched pseudo-primitives
+  bt.K2far = bt.same_centre ? std::min(bt.K2, bt.la + bt.lb + 1) : bt.K2;
+  std::vector<double> prim_far(kPrimFields * (size_t)bt.K2far * st, 0.0);
+  std::vector<PrimPair> cps;
+#endif
   std::vector<int> idx(3 * st, 0);
   std::vector<PrimPair> pps;
   std::vector<int> shA(np), shB(np);
@@ -372,6 +387,18 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
       const double f[kPrimFields] = {pp.zeta, pp.rzeta, pp.Px, pp.Py, pp.Pz, pp.pref, pp.pfar};
       for (int c = 0; c < kPrimFields; ++c) prim[((size_t)c * bt.K2 + k) * st + s] = f[c];
     }
+#if RCHEM_FAR_COMPRESS
+    if (!(bt.same_centre && compress_far_prim_pairs(pps, bt.la + bt.lb, &cps) &&
+          (int)cps.size() == bt.K2far))
+      cps = pps;  // (two-centre pair, or nothing to gain)
+    if ((int)cps.size() != bt.K2far)
+      return fail(RCHEM_ERR_CUDA, "internal: far-field primitive table layout");
+    for (int k = 0; k < bt.K2far; ++k) {
+      const PrimPair& pp = cps[k];
+      const double f[kPrimFields] = {pp.zeta, pp.rzeta, pp.Px, pp.Py, pp.Pz, pp.pref, pp.pfar};
+      for (int c = 0; c < kPrimFields; ++c) prim_far[((size_t)c * bt.K2far + k) * st + s] = f[c];
+    }
+#endif
     const PairBound pb = bound_prim_pairs(pps);
     for (int d = 0; d < 3; ++d) {
       geom[d * st + s] = A.ctr[d];
@@ -388,6 +415,9 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   // padding slots replicate pair 0 so stray reads stay finite
   for (int s = np; s < (int)st; ++s) {
     for (size_t c = 0; c < kPrimFields * (size_t)bt.K2; ++c) prim[c * st + s] = prim[c * st];
+#if RCHEM_FAR_COMPRESS
+    for (size_t c = 0; c < kPrimFields * (size_t)bt.K2far; ++c) prim_far[c * st + s] = prim_far[c * st];
+#endif
     for (int c = 0; c < kGeomFields; ++c) geom[c * st + s] = geom[c * st];
     for (int c = 0; c < 3; ++c) idx[c * st + s] = idx[c * st];
   }
@@ -396,6 +426,9 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   if (!bt.Q.empty()) bt.Q.swap(Q);
   if (!bt.d_prim) {
     CUDA_OK(cudaMalloc(&bt.d_prim, prim.size() * sizeof(double)));
+#if RCHEM_FAR_COMPRESS
+    CUDA_OK(cudaMalloc(&bt.d_prim_far, prim_far.size() * sizeof(double)));
+#endif
     CUDA_OK(cudaMalloc(&bt.d_geom, geom.size() * sizeof(double)));
     CUDA_OK(cudaMalloc(&bt.d_idx, idx.size() * sizeof(int)));
     CUDA_OK(cudaMalloc(&bt.d_Dp, (size_t)bt.ncomp() * st * sizeof(double)));
@@ -404,6 +437,10 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   }
   CUDA_OK(cudaMemcpyAsync(bt.d_prim, prim.data(), prim.size() * sizeof(double),
                           cudaMemcpyHostToDevice, h->stream));
+#if RCHEM_FAR_COMPRESS
+  CUDA_OK(cudaMemcpyAsync(bt.d_prim_far, prim_far.data(), prim_far.size() * sizeof(double),
+                          cudaMemcpyHostToDevice, h->stream));
+#endif
   CUDA_OK(cudaMemcpyAsync(bt.d_geom, geom.data(), geom.size() * sizeof(double),
                           cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaMemcpyAsync(bt.d_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice,
@@ -476,8 +513,14 @@ int ensure_ready(rchem_basis* h) {
       // K2 = number of SIGNIFICANT primitive pairs (pair_build.h kPrimPairEps)
       const int K2 = build_significant_prim_pairs(sh[a], sh[b], h->prim_eps, &scratch_pps);
       const int cls = sh[a].l * (sh[a].l + 1) / 2 + sh[b].l;
-      Batch& bt = by_key[std::make_tuple(cls, -K2, 0)];
-      bt.la = sh[a].l; bt.lb = sh[b].l; bt.K2 = K2;
+#if RCHEM_FAR_COMPRESS
+      const int same = (sh[a].ctr[0] == sh[b].ctr[0] && sh[a].ctr[1] == sh[b].ctr[1] &&
+                        sh[a].ctr[2] == sh[b].ctr[2]) ? 1 : 0;
+#else
+      const int same = 0;
+#endif
+      Batch& bt = by_key[std::make_tuple(cls, -K2, same)];
+      bt.la = sh[a].l; bt.lb = sh[b].l; bt.K2 = K2; bt.same_centre = same;
       bt.shA.push_back(a); bt.shB.push_back(b);
     }
   h->batches.clear();
@@ -612,7 +655,8 @@ int ensure_tasks(rchem_basis* h) {
       EriBlockInfo info{0, 0};
       find_block_launcher(B.la, B.lb, K.la, K.lb, &info);
       tt.smem_bytes = (size_t)2 * (ncart(B.la) + ncart(B.lb)) * h->N * sizeof(double) +
-                      (size_t)B.K2 * sizeof(PrimPair) + (size_t)info.kets_per_block * sizeof(int) + 64;
+                      (size_t)(B.K2 + (RCHEM_FAR_COMPRESS ? B.K2far : 0)) * sizeof(PrimPair) +
+                      (size_t)info.kets_per_block * sizeof(int) + 64;
       const bool rows_fit = tt.smem_bytes <= kMaxBlockSmem && info.threads > 0;
       // a bra pair is "heavy" when its ket prefix fills the block kernel's threads at least
       // kHeavyPasses times; below that the warp-per-bra-pair kernel (no D/K row staging, no
@@ -645,7 +689,8 @@ int ensure_tasks(rchem_basis* h) {
         int cap = 0;
         for (int p = 0; p < B.npairs; ++p)
           if (nq_light[p] > 0) { lp.push_back(p); cap = std::max(cap, nq_light[p]); }
-        const size_t per_warp = (((size_t)B.K2 * sizeof(PrimPair) + (size_t)cap * sizeof(int)) + 7) & ~(size_t)7;
+        const size_t per_warp = (((size_t)(B.K2 + (RCHEM_FAR_COMPRESS ? B.K2far : 0)) * sizeof(PrimPair) +
+                                  (size_t)cap * sizeof(int)) + 7) & ~(size_t)7;
         static const bool kLightKernel = [] {
           const char* e = std::getenv("RCHEM_LIGHT");
           return e ? atoi(e) != 0 : true;
@@ -932,7 +977,7 @@ void rchem_basis_destroy(rchem_basis* h) {
     cudaSetDevice(h->device);
     free_tasks(h);
     for (Batch& bt : h->batches) {
-      cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_idx); cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
+      cudaFree(bt.d_prim); cudaFree(bt.d_prim_far); cudaFree(bt.d_geom); cudaFree(bt.d_idx); cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
     }
     cudaFree(h->d_boys); cudaFree(h->d_delta_thr); cudaFree(h->d_delta_rows); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK); cudaFree(h->d_dmax); cudaFree(h->d_light_tasks); cudaFree(h->d_light_prefix); cudaFreeHost(h->h_light_tasks); cudaFreeHost(h->h_light_prefix);
     cudaFree(h->d_fn_shell); cudaFree(h->d_pair_key); cudaFree(h->d_pair_fwd);

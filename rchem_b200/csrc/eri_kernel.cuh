@@ -45,6 +45,12 @@ enum EriMode : int { kModeJK = 0, kModeTensor = 1, kModeSchwarz = 2 };
 // Schwarz bound Q; idx holds three [stride] int arrays bfA, bfB, diag.
 constexpr int kPrimFields = 7;
 constexpr int kGeomFields = 12;
+// RCHEM_FAR_COMPRESS (round-2 groundwork, default off, NOT yet verified on a GPU): the far-only
+// code reads a second primitive table in which same-centre shell pairs are replaced by their
+// L+1 moment-matched pseudo-primitives (pair_build.h compress_far_prim_pairs).
+#ifndef RCHEM_FAR_COMPRESS
+#define RCHEM_FAR_COMPRESS 0
+#endif
 struct BatchView {
   const double* prim;
   const double* geom;
@@ -54,6 +60,10 @@ struct BatchView {
   int npairs;
   int stride;
   int K2;
+#if RCHEM_FAR_COMPRESS
+  const double* prim_far;  // [kPrimFields][K2far][stride], far-field form only (zeta, pref unused)
+  int K2far;
+#endif
 };
 
 struct EriTask {
@@ -98,6 +108,22 @@ __device__ __forceinline__ PrimPair load_prim(const BatchView& b, int k, int p) 
   return pp;
 }
 
+#if RCHEM_FAR_COMPRESS
+__device__ __forceinline__ PrimPair load_prim_far(const BatchView& b, int k, int p) {
+  const size_t fs = (size_t)b.K2far * b.stride;
+  const double* base = b.prim_far + (size_t)k * b.stride + p;
+  PrimPair pp;
+  pp.zeta = 0.0;
+  pp.rzeta = __ldg(base + fs);
+  pp.Px = __ldg(base + 2 * fs);
+  pp.Py = __ldg(base + 3 * fs);
+  pp.Pz = __ldg(base + 4 * fs);
+  pp.pref = 0.0;
+  pp.pfar = __ldg(base + 6 * fs);
+  return pp;
+}
+#endif
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -130,6 +156,7 @@ template <class C, int LA, int LB, int LC, int LD, int BOYS, bool BRA_SMEM, bool
 __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const BraGeom& g,
                                                 const PrimPair* __restrict__ s_bra, int q,
                                                 double* __restrict__ out, int& bfC, int& bfD) {
+  // (with RCHEM_FAR_COMPRESS and FAR, s_bra points at the bra pair's COMPRESSED primitives)
   constexpr int NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
   constexpr bool kUnroll = C::kOut <= 81;
   const double* gk = t.ket.geom + q;
@@ -144,9 +171,17 @@ __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const B
 #pragma unroll(C::kTargets <= 100 ? C::kTargets : 1)
   for (int i = 0; i < C::kTargets; ++i) acc[i] = 0.0;
 
+#if RCHEM_FAR_COMPRESS
+  const int K2b = FAR ? t.bra.K2far : t.bra.K2, K2k = FAR ? t.ket.K2far : t.ket.K2;
+#else
   const int K2b = t.bra.K2, K2k = t.ket.K2;
+#endif
   for (int kk = 0; kk < K2k; ++kk) {
+#if RCHEM_FAR_COMPRESS
+    const PrimPair pk = FAR ? load_prim_far(t.ket, kk, q) : load_prim(t.ket, kk, q);
+#else
     const PrimPair pk = load_prim(t.ket, kk, q);
+#endif
     for (int kb = 0; kb < K2b; ++kb) {
       if (FAR) {
         primitive_quartet_far<C>(s_bra[kb], pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, acc);
@@ -479,6 +514,14 @@ eri_jk_block_kernel(const EriTask t) {
   double* Krow_b = Krow_a + NA * N;      // [NB][N]
   PrimPair* s_bra = reinterpret_cast<PrimPair*>(Krow_b + NB * N);  // [K2_bra]
   for (int k = tid; k < t.bra.K2; k += T) s_bra[k] = load_prim(t.bra, k, p);
+#if RCHEM_FAR_COMPRESS
+  PrimPair* s_bra_far = s_bra + t.bra.K2;                            // [K2far_bra]
+  for (int k = tid; k < t.bra.K2far; k += T) s_bra_far[k] = load_prim_far(t.bra, k, p);
+  PrimPair* s_bra_end = s_bra_far + t.bra.K2far;
+#else
+  PrimPair* s_bra_far = s_bra;
+  PrimPair* s_bra_end = s_bra + t.bra.K2;
+#endif
   const BraGeom g = load_bra_geom(t.bra, p);
   for (int a = 0; a < NA; ++a)
     for (int j = tid; j < N; j += T) {
@@ -517,7 +560,7 @@ eri_jk_block_kernel(const EriTask t) {
   //     primitive quartet's x from below.  These run the far-only code (primitive_quartet_far);
   //   * grid / corrected: the general code, which handles any x; the split (same lower bound
   //     of x against ref_exact_from(L)) only decides which lanes run together.
-  int* s_list = reinterpret_cast<int*>(s_bra + t.bra.K2);  // [q1 - q0]
+  int* s_list = reinterpret_cast<int*>(s_bra_end);  // [q1 - q0]
   const int nk = q1 - q0;
   {
     const BraBound bb = load_bra_bound(t.bra, p);
@@ -606,7 +649,7 @@ eri_jk_block_kernel(const EriTask t) {
     double out[C::kOut];
     int bfC, bfD;
     const double scale =
-        shell_quartet<C, LA, LB, LC, LD, BOYS, true, true>(t, p, g, s_bra, q, out, bfC, bfD);
+        shell_quartet<C, LA, LB, LC, LD, BOYS, true, true>(t, p, g, s_bra_far, q, out, bfC, bfD);
     digest(q, out, scale, bfC, bfD);
   }
   for (; it < nk; it += T) {
@@ -662,11 +705,22 @@ __device__ __forceinline__ void jk_light_body(const EriTask& t, long long blk, d
   const int nq = __ldg(t.nq + p);
   const int N = t.N, sb = t.bra.stride, sk = t.ket.stride;
 
-  const size_t per_warp = (size_t)t.bra.K2 * sizeof(PrimPair) + (size_t)t.light_cap * sizeof(int);
+#if RCHEM_FAR_COMPRESS
+  const int k2_staged = t.bra.K2 + t.bra.K2far;
+#else
+  const int k2_staged = t.bra.K2;
+#endif
+  const size_t per_warp = (size_t)k2_staged * sizeof(PrimPair) + (size_t)t.light_cap * sizeof(int);
   PrimPair* s_bra = reinterpret_cast<PrimPair*>(reinterpret_cast<char*>(smem) +
                                                 (size_t)wib * ((per_warp + 7) & ~(size_t)7));
-  int* s_list = reinterpret_cast<int*>(s_bra + t.bra.K2);
+  int* s_list = reinterpret_cast<int*>(s_bra + k2_staged);
   for (int k = lane; k < t.bra.K2; k += 32) s_bra[k] = load_prim(t.bra, k, p);
+#if RCHEM_FAR_COMPRESS
+  PrimPair* s_bra_far = s_bra + t.bra.K2;
+  for (int k = lane; k < t.bra.K2far; k += 32) s_bra_far[k] = load_prim_far(t.bra, k, p);
+#else
+  PrimPair* s_bra_far = s_bra;
+#endif
   const BraGeom g = load_bra_geom(t.bra, p);
   const int bfA = __ldg(t.bra.idx + p), bfB = __ldg(t.bra.idx + sb + p);
 
@@ -764,7 +818,7 @@ __device__ __forceinline__ void jk_light_body(const EriTask& t, long long blk, d
     double out[C::kOut];
     int bfC, bfD;
     const double scale =
-        shell_quartet<C, LA, LB, LC, LD, BOYS, true, true>(t, p, g, s_bra, q, out, bfC, bfD);
+        shell_quartet<C, LA, LB, LC, LD, BOYS, true, true>(t, p, g, s_bra_far, q, out, bfC, bfD);
     digest(q, out, scale, bfC, bfD);
   }
   for (; it < nq; it += 32) {
