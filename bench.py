@@ -52,15 +52,28 @@ def parse():
                     help="reference = libpyquante2 Fgamma (1e-12 parity); exact = converged Boys")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle parity block")
+    ap.add_argument("--parity-elements", type=int, default=8)
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------
 # workload + sampling of surviving shell quartets (shared by both arms)
 # ---------------------------------------------------------------------------------------
-def make_workload(name):
-    from rchem_b200 import geometry as geo
+def load_geometry():
+    """rchem_b200/geometry.py loaded BY PATH: the reference arm must not import the package
+    (importing it maps librchem_b200.so into the process)."""
+    import importlib.util
 
+    spec = importlib.util.spec_from_file_location(
+        "_rchem_geometry", os.path.join(ROOT, "rchem_b200", "geometry.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_workload(name):
+    geo = load_geometry()
     n_waters, basis, tau, desc = WORKLOADS[name]
     z, x = geo.water_cluster(n_waters)
     return z, x, basis, tau, desc
@@ -174,6 +187,7 @@ def run_reference(args):
     if orc.ref_lib() is not None:
         orc.use_reference_kernel(True)
         kind = "reference"
+    orc.set_num_threads(host_cores())
     # pair list + Schwarz bounds on the CPU (exact Boys, like the product), by the oracle
     shell_l, shell_first = [], []
     i = 0
@@ -201,7 +215,9 @@ def run_reference(args):
     Q = np.zeros(len(sa))
     np.maximum.at(Q, np.array(owner), np.abs(vals))
     Q = np.sqrt(Q)
-    cores = host_cores()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every core explicitly and report
+    # the thread count OpenMP actually runs with
+    cores = orc.set_num_threads(host_cores())
     per_step = max(2.0, min(args.cpu_seconds, 60.0 / max(1, args.steps + args.warmup)))
     fq, n_shell = sample_shell_quartets(shell_l, shell_first, sa, sb, Q, tau, 20000)
     rates, times = [], []
@@ -213,7 +229,8 @@ def run_reference(args):
     value = float(np.mean(rates))
     sample = (f"{n_shell} seeded random surviving shell quartets of the workload (all Cartesian "
               f"components, all primitives) evaluated {used // n_shell}x per step; libpyquante2 "
-              f"coulomb_repulsion via basis.rs loop order, OpenMP x{cores}")
+              f"coulomb_repulsion via basis.rs loop order, OpenMP x{cores} threads "
+              f"(set explicitly; {host_cores()} cores visible)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -233,6 +250,18 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
+def profile_counters(workload, boys, world):
+    """ncu-derived per-step counters of a workload (DRAM bytes, FP64 warp instructions), from
+    the committed summary profiles/counters.json (written by tools/counters_from_ncu.py from an
+    ncu launch list of this very command); None when that configuration was not profiled."""
+    path = os.path.join(ROOT, "profiles", "counters.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get(f"{workload}/{boys}/{world}")
+    except (OSError, ValueError):
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -253,9 +282,11 @@ def run_ours(args):
     basis = rc.Basis.new(z, x, basis_name)
     basis.set_device(local)
     basis.set_schwarz_tau(tau)
-    basis.set_boys(rc.BOYS_REFERENCE if args.boys == "reference" else rc.BOYS_EXACT)
+    boys_mode = rc.BOYS_REFERENCE if args.boys == "reference" else rc.BOYS_EXACT
+    basis.set_boys(boys_mode)
     n = basis.nbf
-    D_host = torch.from_numpy(geo.synthetic_density(n)).pin_memory()
+    D_np = geo.synthetic_density(n)
+    D_host = torch.from_numpy(D_np).pin_memory()
     D_dev = D_host.to(dev)
     JK_dev = torch.zeros((2, n, n), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
@@ -274,6 +305,7 @@ def run_ours(args):
     J_host = torch.empty((n, n), dtype=torch.float64).pin_memory()
     K_host = torch.empty((n, n), dtype=torch.float64).pin_memory()
     JK_host = torch.empty((2, n, n), dtype=torch.float64).pin_memory()
+    D_in = torch.empty((n, n), dtype=torch.float64, device=dev)
 
     def step_e2e():
         flush.fill_(1.0)
@@ -281,16 +313,26 @@ def run_ours(args):
             # the reference-facing call: JK_direct(&mut J, &mut K, &basis, &D) with host buffers
             rc.JK_direct(J_host.numpy(), K_host.numpy(), basis, D_host.numpy())
         else:
-            d = D_host.to(dev, non_blocking=True)
-            parallel.jk_direct_distributed(basis, d, JK_dev, rank, world)
-            JK_host.copy_(JK_dev, non_blocking=True)
+            # one host: rank 0 alone uploads D and reads J, K back; D travels to the other GPUs
+            # over NVLink (NCCL broadcast), the partial [J|K] come back with the all-reduce
+            if rank == 0:
+                D_in.copy_(D_host, non_blocking=True)
+            dist.broadcast(D_in, src=0)
+            parallel.jk_direct_distributed(basis, D_in, JK_dev, rank, world)
+            if rank == 0:
+                JK_host.copy_(JK_dev, non_blocking=True)
             torch.cuda.synchronize()
 
-    # ---- warm-up (first call also builds pair data, Schwarz bounds and the task tables) ----
-    for _ in range(max(args.warmup, 1)):
+    # ---- first call: builds pair data, Schwarz bounds, Boys tables and the task tables ----------
+    barrier()
+    t0 = time.perf_counter()
+    step_resident()
+    barrier()
+    first_call_ms = 1e3 * (time.perf_counter() - t0)
+    setup_ms = basis.stats()["setup_ms"]
+    for _ in range(max(args.warmup - 1, 0)):
         step_resident()
     barrier()
-    stats0 = basis.stats()
 
     # ---- timed: device-resident -------------------------------------------------------------
     sampler = ClockSampler(local)
@@ -299,14 +341,12 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    t_wall = time.perf_counter()
     for _ in range(args.steps):
         step_resident()
         if rank == 0 and world == 1:
             kernel_ms.append(basis.stats()["kernel_ms"])  # syncs on the library's end event
     e1.record(stream)
     barrier()
-    t_wall = time.perf_counter() - t_wall
     ms_total = e0.elapsed_time(e1)
     if world == 1 and not kernel_ms:
         kernel_ms = [basis.stats()["kernel_ms"]]
@@ -315,22 +355,32 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
+    # checksum of the result every rank holds after the all-reduce (SCALE: N = 2/4/8 must
+    # reproduce N = 1 to rounding)
+    J_res, K_res = JK_dev[0].clone(), JK_dev[1].clone()
+    checksum = {"sum_J": float(J_res.sum().item()), "sum_K": float(K_res.sum().item()),
+                "norm_J": float(torch.linalg.norm(J_res).item()),
+                "norm_K": float(torch.linalg.norm(K_res).item()),
+                "trace_JD": float((J_res * D_dev).sum().item()),
+                "trace_KD": float((K_res * D_dev).sum().item())}
 
     # ---- timed: end to end through the host-buffer API ---------------------------------------
     for _ in range(1):
         step_e2e()
     barrier()
     t0 = time.perf_counter()
-    e0.record(stream)
     for _ in range(args.steps):
         step_e2e()
-    e1.record(stream)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    if world == 1:
+        J_e2e, K_e2e = J_host.numpy().copy(), K_host.numpy().copy()
+    else:
+        J_e2e, K_e2e = JK_host[0].numpy().copy(), JK_host[1].numpy().copy()
     # ---- the other Boys flavour, same workload, device-resident (reported alongside) ----------
     other = rc.BOYS_EXACT if args.boys == "reference" else rc.BOYS_REFERENCE
     basis.set_boys(other)
@@ -346,10 +396,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     other_ms = float(t.item()) / args.steps
     other_kernel_ms = basis.stats()["kernel_ms"]
-    basis.set_boys(rc.BOYS_REFERENCE if args.boys == "reference" else rc.BOYS_EXACT)
+    basis.set_boys(boys_mode)
     clocks = sampler.stop()
 
-    # ---- whole-job counts ---------------------------------------------------------------------
+    # ---- whole-job counts (exact per rank, summed) -------------------------------------------------
     st = basis.stats()
     counts = torch.tensor([st["shell_quartets"], st["prim_quartets"], st["integrals"],
                            st["model_flops"], st["launches"]], dtype=torch.float64, device=dev)
@@ -373,7 +423,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "basis": basis_name, "schwarz_tau": tau, "nbf": n,
-                   "boys": "reference (libpyquante2 Fgamma, 1e-12 parity)" if args.boys == "reference"
+                   "boys": "reference (libpyquante2 Fgamma)" if args.boys == "reference"
                    else "exact (tabulated Taylor; <=2e-8 from libpyquante2)",
                    "shell_quartets_per_step": sq, "shell_quartets_unscreened": st["shell_quartets_all"],
                    "primitive_quartets_per_step": pq, "integrals_per_step": ints,
@@ -382,13 +432,19 @@ def run_ours(args):
         "integrals_per_s": ints / (ms_per_step * 1e-3),
         "primitive_quartets_per_s": pq / (ms_per_step * 1e-3),
         "jk_build_ms": ms_per_step,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n * n * world,
-                "d2h_bytes_per_step": 16 * n * n * (world if world > 1 else 1),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n * n,
+                "d2h_bytes_per_step": 16 * n * n,
                 "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "rchem_jk_direct (host buffers)" if world == 1 else
-                       "pinned D -> H2D -> rchem_jk_direct_device + all-reduce -> D2H"},
+                       "rank 0: pinned D -> H2D, NCCL broadcast of D; every rank: "
+                       "rchem_jk_direct_device; all-reduce of [J|K]; rank 0: D2H"},
         "gpu_launches": int(launches * args.steps),
         "clocks": clocks,
+        "setup": {"first_call_ms": first_call_ms, "library_setup_ms": setup_ms,
+                  "note": "one-off per basis, outside the timed steps: shell-pair batches, Schwarz "
+                          "bounds (GPU), Boys tables, implicit quartet-list tables; first_call_ms = "
+                          "first J/K build including all of it"},
+        "checksum": checksum,
     }
     # ---- roofline: FP64 pipe --------------------------------------------------------------------
     if world == 1:
@@ -405,14 +461,13 @@ def run_ours(args):
         "roofline_frac": (flops / ((other_kernel_ms if world == 1 else other_ms) * 1e-3) / 1e12
                           / (world if world > 1 else 1)) / peak_avg,
     }
+    prof = profile_counters(args.workload, args.boys, world)
     line["roofline"] = {
         "bound": "fp64", "achieved": achieved, "peak": peak_avg, "unit": "TFLOP/s",
         "frac": achieved / peak_avg,
-        # DRAM bytes of one step (all ERI launches), from the committed ncu launch list
-        # profiles/r01_launch_summary_h2o96_631g_ref_final.txt (headline workload, 1 GPU,
-        # reference Boys); null for other workloads / GPU counts
-        "traffic": 1.43e9 if (args.workload == DEFAULT_WORKLOAD and world == 1) else None,
-        "peak_source": "measured in this run: DFMA microbenchmark rchem_fp64_peak (avg of 10; "
+        "traffic": prof["dram_bytes_per_step"] if prof else None,
+        "traffic_source": prof["source"] if prof else None,
+        "peak_source": "builder-measured in this run: DFMA microbenchmark rchem_fp64_peak (avg of 10; "
                        f"best {peak_best:.2f}); MEASURED_PEAKS.json has no FP64 entry",
         "kernel": "eri_jk_block_kernel<la,lb,lc,ld,boys> + eri_jk_light_multi_kernel<..> (all class "
                   "instantiations of one step; the (ps|ss) block kernel is the largest share)",
@@ -421,6 +476,34 @@ def run_ours(args):
         "flop_model": "SURVEY 8(d): sum over surviving quartets of K2_bra*K2_ket*P(class)+H(class)",
         "per_gpu": world > 1,
     }
+    if prof and prof.get("fp64_warp_inst_per_step"):
+        # instruction-based view: FP64 warp instructions actually executed (ncu) against the
+        # FP64 pipe's issue rate (2 warp instructions per SM and clock = 64 lanes) over the LIVE
+        # step time -- independent of the flop model
+        sm_hz = 1e6 * (clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965.0)
+        line["roofline"]["fp64_pipe_active"] = (
+            prof["fp64_warp_inst_per_step"] / world / (148 * 2.0 * sm_hz * k_ms * 1e-3))
+        line["roofline"]["fp64_pipe_active_source"] = (
+            "FP64 warp instructions per step from " + prof["source"] + " over the live kernel time")
+    # ---- parity: sampled J/K elements of THIS run's result against oracle rows -----------------
+    if not args.no_parity:
+        from oracle import oracle as orc
+        from oracle import parity
+
+        if orc.ref_lib() is not None:
+            orc.use_reference_kernel(True)
+        orc.set_num_threads(host_cores())
+        obasis = orc.make_basis(z, x, basis_name)
+        t0 = time.perf_counter()
+        ej, ek, elements = parity.sampled_jk_errors(orc, obasis, basis, D_np, J_e2e, K_e2e, tau,
+                                                    count=args.parity_elements)
+        line["parity"] = {
+            "max_abs_err": max(ej, ek), "max_abs_err_J": ej, "max_abs_err_K": ek,
+            "tolerance": 1e-12, "elements": len(elements),
+            "checked": "J[mu,nu], K[mu,nu] of the e2e (host-buffer) result vs rows rebuilt from "
+                       "oracle integrals (libpyquante2 coulomb_repulsion when oracle/_ref is present) "
+                       "under the same Schwarz list; outside the timed region",
+            "boys": args.boys, "seconds": time.perf_counter() - t0}
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
@@ -429,16 +512,17 @@ def run_ours(args):
         if orc.ref_lib() is not None:
             orc.use_reference_kernel(True)
             kind = "reference"
+        threads = orc.set_num_threads(host_cores())
         obasis = orc.make_basis(z, x, basis_name)
         sa, sb, _, Q = basis.schwarz()
         l, first = basis.shells()
         fq, n_shell = sample_shell_quartets(l, first, sa, sb, Q, tau, 20000)
         rate, used, dt = cpu_time_sample(orc, obasis, fq, n_shell, args.cpu_seconds)
         line["cpu_baseline"] = {
-            "value": rate, "unit": UNIT, "cores": host_cores(), "kind": kind,
+            "value": rate, "unit": UNIT, "cores": threads, "kind": kind,
             "sample": f"{n_shell} seeded random surviving shell quartets of the workload, all "
                       f"components and primitives, evaluated {used // n_shell}x ({dt:.1f} s); "
-                      "libpyquante2 coulomb_repulsion in basis.rs loop order, OpenMP"}
+                      f"libpyquante2 coulomb_repulsion in basis.rs loop order, OpenMP x{threads}"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

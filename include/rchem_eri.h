@@ -87,6 +87,18 @@ int64_t rchem_ijkl2intindex(int64_t i, int64_t j, int64_t k, int64_t l);
                                    pairs' bounding spheres and evaluate those by the point-
                                    multipole form; 0: every quartet through the general code
                                    (same results to ~1e-15; a tuning / cross-check knob)        */
+#define RCHEM_OPT_HEAVY_PASSES 6 /* J/K kernel choice: a bra pair whose surviving ket prefix fills
+                                   the block kernel's threads at least this many times (default 2)
+                                   goes to the block-per-bra-pair kernel, the others to the
+                                   warp-per-bra-pair kernel; 0 sends every bra pair with >= 1 ket to
+                                   the block kernel.  Same results either way (a tuning knob, and
+                                   how the tests force each kernel).                            */
+#define RCHEM_OPT_LIGHT_KERNEL 8 /* 1 (default): bra pairs below the heavy threshold use the
+                                   warp-per-bra-pair kernel; 0: the warp-per-32-kets chunk kernel
+                                   (the fallback of classes without a block kernel)            */
+#define RCHEM_OPT_SYMMETRIC_D_ONLY 7 /* 1: rchem_jk_direct rejects an asymmetric D with
+                                   RCHEM_ERR_ASYMMETRIC_D instead of paying a second build
+                                   (default 0: any D is accepted, like basis.rs:383-428)       */
 int rchem_set_option(rchem_basis* b, int key, double value);
 double rchem_get_option(const rchem_basis* b, int key);
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream).  The value is used as
@@ -100,8 +112,10 @@ int rchem_use_own_stream(rchem_basis* b);
 /* build_I(&basis) -> dense row-major I[mu][nu][la][si], N^4 doubles       basis.rs:430-460 */
 int rchem_build_I(rchem_basis* b, double* I_host);
 /* JK_direct(&mut J, &mut K, &basis, &D): J,K (N x N) are overwritten       basis.rs:383-428
- * D must be symmetric (the reference's caller passes D = C C^T, rchem.rs:101-104);
- * an asymmetric D returns RCHEM_ERR_ASYMMETRIC_D. */
+ * Any D is accepted, like the reference.  The kernels exploit D = D^T (what the reference's
+ * caller passes: D = C C^T, rchem.rs:101-104); a D that is not symmetric (checked on the
+ * device, relative 1e-14) is split into its symmetric and antisymmetric parts and costs a
+ * second build: J(D) = J(S), K(D) = K(S) + K(A). */
 int rchem_jk_direct(rchem_basis* b, const double* D_host, double* J_host, double* K_host);
 /* JK_inmem(&I, &D) -> (J, K)                                               basis.rs:462-484 */
 int rchem_jk_inmem(int n, const double* I_host, const double* D_host, double* J_host,
@@ -110,7 +124,10 @@ int rchem_jk_inmem(int n, const double* I_host, const double* D_host, double* J_
 /* ---------------- the hot path, DEVICE buffers (no copies; asynchronous on the stream) - */
 int rchem_build_I_device(rchem_basis* b, double* I_dev);
 /* This rank's additive share of J and K: JK_dev holds J then K (2*N*N doubles).  With
- * nranks > 1 the caller sums JK_dev over ranks (one allreduce); rank 0 of 1 gives J, K. */
+ * nranks > 1 the caller sums JK_dev over ranks (one allreduce); rank 0 of 1 gives J, K.
+ * D_dev MUST be symmetric here (no check, no copy: this is the asynchronous inner call;
+ * rchem_jk_direct is the entry point that accepts any D).  The work is enqueued on the handle's
+ * stream (rchem_set_stream): bind it to the stream that produces D_dev / consumes JK_dev. */
 int rchem_jk_direct_device(rchem_basis* b, const double* D_dev, double* JK_dev, int rank,
                            int nranks);
 int rchem_jk_inmem_device(int n, const double* I_dev, const double* D_dev, double* JK_dev,
@@ -146,6 +163,8 @@ typedef struct {
   double kernel_ms;           /* device time of the ERI kernels (CUDA events on the stream) */
   int32_t launches;           /* kernels launched (ERI + finalize)                         */
   int32_t n_tasks;            /* batch pairs                                               */
+  double setup_ms;            /* host wall time spent so far on one-off set-up of this handle:
+                                 pair batches, Schwarz bounds, Boys tables, task tables      */
 } rchem_stats;
 int rchem_get_stats(const rchem_basis* b, rchem_stats* out);
 

@@ -70,6 +70,10 @@ def lib():
         L.orc_jk_inmem.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
         L.orc_eval_quartets.restype = C.c_double
         L.orc_eval_quartets.argtypes = basis_args + [_ip, C.c_int64, C.c_void_p, C.c_int]
+        L.orc_set_num_threads.restype = None
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_get_max_threads.restype = C.c_int
+        L.orc_get_max_threads.argtypes = []
         L.orc_set_reference_kernel.restype = None
         L.orc_set_reference_kernel.argtypes = [C.c_void_p]
         L.orc_one_electron.restype = None
@@ -104,6 +108,13 @@ def ref_lib():
         _ref.ijkl2intindex.restype = i
         _ref.ijkl2intindex.argtypes = [i] * 4
     return _ref
+
+
+def set_num_threads(n):
+    """OpenMP threads of the oracle's loops (torchrun exports OMP_NUM_THREADS=1); returns the
+    thread count actually in effect."""
+    lib().orc_set_num_threads(int(n))
+    return int(lib().orc_get_max_threads())
 
 
 def use_reference_kernel(on=True):

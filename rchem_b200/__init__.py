@@ -28,6 +28,7 @@ LIB_PATH = os.environ.get("RCHEM_B200_LIB") or os.path.join(_HERE, "librchem_b20
 
 BOYS_REFERENCE, BOYS_EXACT = 0, 1
 OPT_BOYS, OPT_SCHWARZ_TAU, OPT_DEVICE, OPT_PRIM_EPS, OPT_FAR_SCHED = 1, 2, 3, 4, 5
+OPT_HEAVY_PASSES, OPT_SYMMETRIC_D_ONLY, OPT_LIGHT_KERNEL = 6, 7, 8
 
 
 class RchemError(RuntimeError):
@@ -51,7 +52,7 @@ class Stats(C.Structure):
     _fields_ = [("shell_quartets", C.c_int64), ("shell_quartets_all", C.c_int64),
                 ("prim_quartets", C.c_int64), ("integrals", C.c_int64),
                 ("model_flops", C.c_double), ("kernel_ms", C.c_double),
-                ("launches", C.c_int32), ("n_tasks", C.c_int32)]
+                ("launches", C.c_int32), ("n_tasks", C.c_int32), ("setup_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -209,6 +210,20 @@ class Basis:
         """Far-field scheduling of the J/K kernels (default on; off = general code only)."""
         _check(_lib.rchem_set_option(self._h, OPT_FAR_SCHED, 1.0 if on else 0.0))
 
+    def set_heavy_passes(self, passes):
+        """J/K kernel choice (RCHEM_OPT_HEAVY_PASSES): bra pairs whose ket prefix fills the block
+        kernel's threads `passes` times go to the block kernel (0 = every bra pair; a huge
+        value = none, i.e. the warp-per-bra-pair / chunk kernels).  Same results."""
+        _check(_lib.rchem_set_option(self._h, OPT_HEAVY_PASSES, float(passes)))
+
+    def set_light_kernel(self, on):
+        """Light bra pairs: warp-per-bra-pair kernel (default) or the chunk kernel."""
+        _check(_lib.rchem_set_option(self._h, OPT_LIGHT_KERNEL, 1.0 if on else 0.0))
+
+    def set_symmetric_only(self, on):
+        """Reject an asymmetric D in JK_direct instead of paying a second build."""
+        _check(_lib.rchem_set_option(self._h, OPT_SYMMETRIC_D_ONLY, 1.0 if on else 0.0))
+
     def set_device(self, ordinal):
         _check(_lib.rchem_set_option(self._h, OPT_DEVICE, float(ordinal)))
 
@@ -245,6 +260,8 @@ class Basis:
 
     # --- device-buffer entry points (raw pointers, e.g. torch tensor .data_ptr()) -------
     def jk_direct_device(self, D_ptr, JK_ptr, rank=0, nranks=1):
+        """Asynchronous on the handle's stream: call set_stream() with the stream that produces
+        D and consumes JK first (parallel.jk_direct_distributed does).  D must be symmetric."""
         _check(_lib.rchem_jk_direct_device(self._h, _vp(D_ptr), _vp(JK_ptr), rank, nranks))
 
     def build_I_device(self, I_ptr):
@@ -285,7 +302,7 @@ def build_I(basis_set):
 
 def JK_direct(J, K, basis_set, D):
     """basis::JK_direct(&mut J, &mut K, &basis_set, &D): J and K are overwritten in place
-    (basis.rs:383-428).  D must be symmetric."""
+    (basis.rs:383-428).  Any D is accepted; one that is not symmetric costs a second build."""
     n = basis_set.nbf
     for name, m in (("J", J), ("K", K)):
         if m.shape != (n, n) or m.dtype != np.float64 or not m.flags["C_CONTIGUOUS"]:

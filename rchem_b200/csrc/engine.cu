@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -73,7 +74,8 @@ int fail_public(int code, const std::string& msg) { return fail(code, msg); }
 // one_electron.cu
 int one_electron_host(int n, const double* origins, const int* powers, const int* prim_offset,
                       const double* exps, const double* coefs, const double* norms, int which,
-                      int natoms, const double* atomcoords, const double* charges, double* M);
+                      int natoms, const double* atomcoords, const double* charges, double* M,
+                      int device);
 #define CUDA_OK(expr)                                                                      \
   do {                                                                                     \
     cudaError_t e_ = (expr);                                                               \
@@ -173,7 +175,69 @@ struct TaskTable {
   int* d_lp = nullptr;
   int nlight = 0, light_cap = 0;
   size_t light_smem = 0;
+  // host copies of the split, for the exact per-rank statistics (quartets_of_rank)
+  std::vector<int> h_nq_light, h_lp, h_hp;
+  std::vector<long long> h_hblk;
+  int kets_per_block = 0;
+  // cache: shell quartets this rank evaluates in each kernel family
+  int stat_rank = -1, stat_nranks = -1;
+  long long q_tensor_mine = 0, q_light_mine = 0, q_heavy_mine = 0;
 };
+
+// Shell quartets of the 32-ket chunks [w0, w0 + nw) of one bra pair with nq kets that belong to
+// `rank`: the chunk kernel gives thread block b (4 consecutive chunks of the task) to rank
+// b % nranks (eri_kernel.cuh eri_kernel).  All chunks are full except the last one.
+static long long owned_chunk_quartets(long long w0, long long nw, int nq, int rank, int nranks) {
+  if (nw <= 0) return 0;
+  auto owned_below = [&](long long w) {  // chunks in [0, w) owned by rank
+    const long long nb = w / kWarpsPerBlock, rem = w % kWarpsPerBlock;
+    long long full = nb > rank ? (nb - rank + nranks - 1) / nranks : 0;  // whole blocks owned
+    return full * kWarpsPerBlock + ((nb % nranks) == rank ? rem : 0);
+  };
+  const long long owned = owned_below(w0 + nw) - owned_below(w0);
+  const long long last = w0 + nw - 1;
+  const bool last_mine = ((last / kWarpsPerBlock) % nranks) == rank;
+  return owned * 32 - (last_mine ? (nw * 32 - nq) : 0);
+}
+
+// Exact shell-quartet counts of rank `rank` of `nranks` for one task (cached in the table).
+static void quartets_of_rank(TaskTable& tt, int rank, int nranks) {
+  if (tt.stat_rank == rank && tt.stat_nranks == nranks) return;
+  tt.stat_rank = rank; tt.stat_nranks = nranks;
+  tt.q_tensor_mine = tt.q_light_mine = tt.q_heavy_mine = 0;
+  const int np = (int)tt.h_nq.size();
+  if (nranks == 1) {
+    tt.q_tensor_mine = tt.nquartets;
+    tt.q_light_mine = tt.nquartets_light;
+    tt.q_heavy_mine = tt.nquartets - tt.nquartets_light;
+    return;
+  }
+  for (int p = 0; p < np; ++p)
+    tt.q_tensor_mine += owned_chunk_quartets(tt.h_prefix[p], tt.h_prefix[p + 1] - tt.h_prefix[p],
+                                             tt.h_nq[p], rank, nranks);
+  if (tt.nlight > 0) {
+    // warp-per-bra-pair kernel: light entry i runs in block i / 4, block b -> rank b % nranks
+    for (int i = 0; i < tt.nlight; ++i)
+      if ((i / kWarpsPerBlock) % nranks == rank) tt.q_light_mine += tt.h_nq_light[tt.h_lp[i]];
+  } else {
+    long long w0 = 0;
+    for (int p = 0; p < np; ++p) {
+      const long long nw = (tt.h_nq_light[p] + 31) / 32;
+      tt.q_light_mine += owned_chunk_quartets(w0, nw, tt.h_nq_light[p], rank, nranks);
+      w0 += nw;
+    }
+  }
+  for (size_t hh = 0; hh < tt.h_hp.size(); ++hh) {
+    // block kernel: heavy entry hh owns blocks [hblk[hh], hblk[hh+1]), each `per` kets
+    const int nq = tt.h_nq[tt.h_hp[hh]];
+    const long long first = tt.h_hblk[hh];
+    const int nb = (int)(tt.h_hblk[hh + 1] - first);
+    const int per = (((nq + nb - 1) / nb) + 31) & ~31;
+    for (int j = 0; j < nb; ++j)
+      if ((first + j) % nranks == rank)
+        tt.q_heavy_mine += std::max(0, std::min(nq, (j + 1) * per) - j * per);
+  }
+}
 
 // D blocks of every shell pair of a batch, pair-major packed: Dp[ab][p] = D[bfA+a][bfB+b]
 __global__ void pack_d_kernel(const double* __restrict__ D, int N, const int* __restrict__ idx,
@@ -214,13 +278,48 @@ __global__ void absmax_kernel(const double* __restrict__ D, size_t n, unsigned l
   if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
-__global__ void finalize_k_kernel(const double* __restrict__ Kh, double* __restrict__ K, int N) {
-  // K = Kh + Kh^T  (the two transposed halves of the 8-fold digestion)
+// K = Kh + sign Kh^T: the two transposed halves of the 8-fold digestion.  sign = +1 for a
+// symmetric density; for an ANTISYMMETRIC density the transposed half changes sign
+// (K[c,a] += (cd|ab) D[d,b] = -(ab|cd) D[b,d]) and the result is ADDED to K (rchem_jk_direct).
+__global__ void finalize_k_kernel(const double* __restrict__ Kh, double* __restrict__ K, int N,
+                                  double sign, int accumulate) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nn = (size_t)N * N;
   if (idx >= nn) return;
   const size_t i = idx / N, j = idx % N;
-  K[idx] = Kh[idx] + Kh[j * N + i];
+  const double v = fma(sign, Kh[j * N + i], Kh[idx]);
+  K[idx] = accumulate ? K[idx] + v : v;
+}
+
+// {max|D|, max|D - D^T|} as bit patterns (non-negative doubles order like their bits), and the
+// split D = S + A into symmetric and antisymmetric parts
+__global__ void asym_probe_kernel(const double* __restrict__ D, int N, unsigned long long* out) {
+  const size_t nn = (size_t)N * N;
+  unsigned long long m = 0, a = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / N, c = i % N;
+    const double v = D[i];
+    m = max(m, (unsigned long long)__double_as_longlong(fabs(v)));
+    if (c < r) a = max(a, (unsigned long long)__double_as_longlong(fabs(v - D[c * N + r])));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    a = max(a, __shfl_xor_sync(0xffffffffu, a, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (m) atomicMax(out, m);
+    if (a) atomicMax(out + 1, a);
+  }
+}
+__global__ void split_density_kernel(const double* __restrict__ D, int N, double* __restrict__ S,
+                                     double* __restrict__ A) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * N) return;
+  const size_t i = idx / N, j = idx % N;
+  const double x = D[idx], y = D[j * N + i];
+  S[idx] = 0.5 * (x + y);
+  A[idx] = 0.5 * (x - y);
 }
 
 // Dense-tensor completion (build_I, basis.rs:451-454 plus the bra<->ket swap): the ERI kernels
@@ -317,6 +416,14 @@ struct rchem_basis {
   double tau = 0.0;
   double prim_eps = kPrimPairEps;
   int device = 0;
+  int light_kernel = [] {  // RCHEM_OPT_LIGHT_KERNEL; the environment sets the default (tuning)
+    const char* e = std::getenv("RCHEM_LIGHT");
+    return e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }();
+  double heavy_passes = [] {  // RCHEM_OPT_HEAVY_PASSES; the environment sets the default (tuning)
+    const char* e = std::getenv("RCHEM_HEAVY_PASSES");
+    return e ? std::max(0.0, atof(e)) : 2.0;
+  }();
   int far_sched = [] {  // RCHEM_OPT_FAR_SCHED; the environment sets the default (tuning)
     const char* e = std::getenv("RCHEM_FAR");
     return e ? (atoi(e) != 0 ? 1 : 0) : 1;
@@ -347,6 +454,14 @@ struct rchem_basis {
   long long* d_pair_key = nullptr;
   unsigned char* d_pair_fwd = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_stream = nullptr;  // orders a build after the previous one across rchem_set_stream
+  double* d_asym = nullptr;         // {max|D|, max|D - D^T|} of the host-buffer entry point
+  double setup_ms = 0.0;            // host wall time of pair build + Schwarz + task tables
+  cudaStream_t last_stream = nullptr;  // stream of the previous build (order_after_previous_build)
+  bool last_stream_valid = false;
+  int symmetric_only = 0;           // RCHEM_OPT_SYMMETRIC_D_ONLY
+  double tasks_heavy = -1.0;        // values the task tables were built with
+  int tasks_light = -1;
   // The tasks of one J/K (or tensor) build are independent kernels; they are spread over a
   // few auxiliary streams so the tail of one launch overlaps the head of the next.
   static constexpr int kAuxStreams = 16;  // upper bound; n_aux (6 or 12, RCHEM_STREAMS) are used
@@ -461,8 +576,42 @@ void fill_common(const rchem_basis* h, EriTask* t) {
     for (int k = 0; k < 6; ++k) t->compscale[l][k] = (l <= h->shells.lmax) ? h->shells.compscale[l][k] : 1.0;
 }
 
+void free_tasks(rchem_basis* h);
+
+// Releases every device-side resource of the handle (by non-null pointer, so it is safe after
+// a partially failed ensure_ready) except the handle's own stream.
+void release_device_state(rchem_basis* h) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return; }
+  if (h->device >= 0 && h->device < ndev) cudaSetDevice(h->device);
+  free_tasks(h);
+  for (Batch& bt : h->batches) {
+    cudaFree(bt.d_prim); cudaFree(bt.d_prim_far); cudaFree(bt.d_geom); cudaFree(bt.d_idx);
+    cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
+  }
+  h->batches.clear();
+  auto drop = [](auto*& ptr) { if (ptr) cudaFree(ptr); ptr = nullptr; };
+  drop(h->d_boys); drop(h->d_delta_thr); drop(h->d_delta_rows); drop(h->d_D); drop(h->d_Kh);
+  drop(h->d_JK); drop(h->d_dmax); drop(h->d_light_tasks); drop(h->d_light_prefix);
+  drop(h->d_fn_shell); drop(h->d_pair_key); drop(h->d_pair_fwd); drop(h->d_asym);
+  if (h->h_light_tasks) cudaFreeHost(h->h_light_tasks);
+  if (h->h_light_prefix) cudaFreeHost(h->h_light_prefix);
+  h->h_light_tasks = nullptr; h->h_light_prefix = nullptr; h->light_tasks_cap = 0;
+  auto drop_ev = [](cudaEvent_t& e) { if (e) cudaEventDestroy(e); e = nullptr; };
+  drop_ev(h->ev0); drop_ev(h->ev1); drop_ev(h->ev_fork); drop_ev(h->ev_light); drop_ev(h->ev_stream);
+  for (int i = 0; i < rchem_basis::kAuxStreams; ++i) {
+    drop_ev(h->ev_join[i]);
+    if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
+    h->aux[i] = nullptr;
+  }
+  h->ready = false;
+  cudaGetLastError();  // nothing above may leave a latched error behind
+}
+
 int ensure_ready(rchem_basis* h) {
   if (h->ready) return RCHEM_OK;
+  const auto t_setup0 = std::chrono::steady_clock::now();
+  release_device_state(h);  // (a previous attempt may have failed half-way)
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -572,6 +721,9 @@ int ensure_ready(rchem_basis* h) {
     h->kbound = 16.0 * *std::max_element(R.begin(), R.end());
   }
   CUDA_OK(cudaMalloc(&h->d_dmax, sizeof(double)));
+  CUDA_OK(cudaMalloc(&h->d_asym, 2 * sizeof(double)));
+  CUDA_OK(cudaEventCreateWithFlags(&h->ev_stream, cudaEventDisableTiming));
+  h->last_stream_valid = false;
   const size_t nn = (size_t)h->N * h->N;
   CUDA_OK(cudaMalloc(&h->d_D, nn * sizeof(double)));
   CUDA_OK(cudaMalloc(&h->d_Kh, nn * sizeof(double)));
@@ -601,6 +753,7 @@ int ensure_ready(rchem_basis* h) {
     CUDA_OK(cudaMemcpy(h->d_pair_fwd, fwd.data(), fwd.size(), cudaMemcpyHostToDevice));
   }
   h->ready = true;
+  h->setup_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup0).count();
   return RCHEM_OK;
 }
 
@@ -623,7 +776,10 @@ void free_tasks(rchem_basis* h) {
 //   q < nq[p] = #{q : Q_bra[p]*Q_ket[q] >= tau}   (Q_ket descending), and q <= p when the
 // batches coincide.  Pure integer/compare work on the shared Q arrays.
 int ensure_tasks(rchem_basis* h) {
-  if (h->tasks_tau == h->tau && !h->tasks.empty()) return RCHEM_OK;
+  if (h->tasks_tau == h->tau && h->tasks_heavy == h->heavy_passes &&
+      h->tasks_light == h->light_kernel && !h->tasks.empty())
+    return RCHEM_OK;
+  const auto t_setup0 = std::chrono::steady_clock::now();
   free_tasks(h);
   const double tau = h->tau;
   for (int bi = 0; bi < (int)h->batches.size(); ++bi)
@@ -661,16 +817,14 @@ int ensure_tasks(rchem_basis* h) {
       // a bra pair is "heavy" when its ket prefix fills the block kernel's threads at least
       // kHeavyPasses times; below that the warp-per-bra-pair kernel (no D/K row staging, no
       // block-wide barriers) is the faster home
-      static const double kHeavyPasses = [] {  // tuning knob; measured on (H2O)96/6-31G with
-        // the light kernel: 0.25: 176 ms, 0.5: 151, 1: 138, 1.5: 135, 2: 135, 3: 136, 4: 146
-        const char* e = std::getenv("RCHEM_HEAVY_PASSES");
-        return e ? std::max(0.01, atof(e)) : 2.0;
-      }();
+      // (RCHEM_OPT_HEAVY_PASSES; measured on (H2O)96/6-31G with the light kernel:
+      // 0.25: 176 ms, 0.5: 151, 1: 138, 1.5: 135, 2: 135, 3: 136, 4: 146)
+      const double kHeavyPasses = h->heavy_passes;
       std::vector<int> nq_light(B.npairs), hp;
       std::vector<long long> prefix_light(B.npairs + 1, 0), hblk(1, 0);
       for (int p = 0; p < B.npairs; ++p) {
         const int cut = tt.h_nq[p];
-        const bool heavy = rows_fit && cut >= (int)(kHeavyPasses * info.threads);
+        const bool heavy = rows_fit && cut >= 1 && (double)cut >= kHeavyPasses * info.threads;
         nq_light[p] = heavy ? 0 : cut;
         prefix_light[p + 1] = prefix_light[p] + (nq_light[p] + 31) / 32;
         if (heavy) {
@@ -691,12 +845,9 @@ int ensure_tasks(rchem_basis* h) {
           if (nq_light[p] > 0) { lp.push_back(p); cap = std::max(cap, nq_light[p]); }
         const size_t per_warp = (((size_t)(B.K2 + (RCHEM_FAR_COMPRESS ? B.K2far : 0)) * sizeof(PrimPair) +
                                   (size_t)cap * sizeof(int)) + 7) & ~(size_t)7;
-        static const bool kLightKernel = [] {
-          const char* e = std::getenv("RCHEM_LIGHT");
-          return e ? atoi(e) != 0 : true;
-        }();
-        if (kLightKernel && info.threads > 0 && !lp.empty() && per_warp * kWarpsPerBlock <= 40 * 1024) {
+        if (h->light_kernel && info.threads > 0 && !lp.empty() && per_warp * kWarpsPerBlock <= 40 * 1024) {
           tt.nlight = (int)lp.size();
+          tt.h_lp = lp;
           tt.light_cap = cap;
           tt.light_smem = per_warp * kWarpsPerBlock;
           CUDA_OK(cudaMalloc(&tt.d_lp, lp.size() * sizeof(int)));
@@ -705,6 +856,10 @@ int ensure_tasks(rchem_basis* h) {
       }
       tt.nheavy = (int)hp.size();
       tt.nblocks_heavy = hblk.back();
+      tt.kets_per_block = info.kets_per_block;
+      tt.h_nq_light = nq_light;
+      tt.h_hp = hp;
+      tt.h_hblk = hblk;
       CUDA_OK(cudaMalloc(&tt.d_prefix_light, prefix_light.size() * sizeof(long long)));
       CUDA_OK(cudaMalloc(&tt.d_nq_light, std::max<size_t>(1, nq_light.size()) * sizeof(int)));
       CUDA_OK(cudaMalloc(&tt.d_hp, std::max<size_t>(1, hp.size()) * sizeof(int)));
@@ -722,6 +877,9 @@ int ensure_tasks(rchem_basis* h) {
       h->tasks.push_back(std::move(tt));
     }
   h->tasks_tau = tau;
+  h->tasks_heavy = h->heavy_passes;
+  h->tasks_light = h->light_kernel;
+  h->setup_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup0).count();
   return RCHEM_OK;
 }
 
@@ -768,12 +926,20 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
     if (total > 0) {
       if (total > h->light_tasks_cap) {
         if (h->ev_light) CUDA_OK(cudaEventSynchronize(h->ev_light));
-        if (h->d_light_tasks) { cudaFree(h->d_light_tasks); cudaFree(h->d_light_prefix); cudaFreeHost(h->h_light_tasks); cudaFreeHost(h->h_light_prefix); cudaFreeHost(h->h_light_tasks); cudaFreeHost(h->h_light_prefix); }
-        h->light_tasks_cap = total;
+        // each buffer is released exactly once and forgotten before the reallocation, so a
+        // failed cudaMalloc below cannot leave a stale pointer for rchem_basis_destroy
+        if (h->d_light_tasks) CUDA_OK(cudaFree(h->d_light_tasks));
+        if (h->d_light_prefix) CUDA_OK(cudaFree(h->d_light_prefix));
+        if (h->h_light_tasks) CUDA_OK(cudaFreeHost(h->h_light_tasks));
+        if (h->h_light_prefix) CUDA_OK(cudaFreeHost(h->h_light_prefix));
+        h->d_light_tasks = nullptr; h->d_light_prefix = nullptr;
+        h->h_light_tasks = nullptr; h->h_light_prefix = nullptr;
+        h->light_tasks_cap = 0;
         CUDA_OK(cudaMalloc(&h->d_light_tasks, total * sizeof(EriTask)));
         CUDA_OK(cudaMalloc(&h->d_light_prefix, (2 * total + 64) * sizeof(int)));
         CUDA_OK(cudaMallocHost(&h->h_light_tasks, total * sizeof(EriTask)));
         CUDA_OK(cudaMallocHost(&h->h_light_prefix, (2 * total + 64) * sizeof(int)));
+        h->light_tasks_cap = total;
         if (!h->ev_light) CUDA_OK(cudaEventCreateWithFlags(&h->ev_light, cudaEventDisableTiming));
       } else {
         CUDA_OK(cudaEventSynchronize(h->ev_light));  // the previous build's copy has left the buffer
@@ -832,17 +998,17 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
                 (unsigned)g.grid, g.smem, pick_stream()));
     st.launches += 1;
   }
-  for (const TaskTable& tt : h->tasks) {
+  for (TaskTable& tt : h->tasks) {
     const Batch &B = h->batches[tt.bra], &K = h->batches[tt.ket];
     st.shell_quartets_all += tt.nquartets_all;
     if (tt.nwarps == 0) continue;
+    quartets_of_rank(tt, rank, nranks);
     EriTask t = make_task(tt);
     EriLaunchFn fn = find_launcher(B.la, B.lb, K.la, K.lb);
     if (!fn) return fail(RCHEM_ERR_UNSUPPORTED_AM, "no kernel for this class");
     const FlopModel* fm = flop_model(B.la, B.lb, K.la, K.lb);
     const double k4 = (double)B.K2 * K.K2;
-    auto account = [&](double quartets) {
-      const long long q = (long long)std::llround(quartets);
+    auto account = [&](long long q) {
       st.shell_quartets += q;
       st.prim_quartets += (long long)(q * k4);
       st.integrals += q * (long long)(ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb));
@@ -862,7 +1028,7 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
         CUDA_OK(lfn(h->boys, t, (unsigned)mine, tt.light_smem, pick_stream()));
         if (mine > 0) st.launches += 1;
       }
-      account(tt.nquartets_light * (double)mine / (double)nblocks);
+      account(tt.q_light_mine);
     } else if (nwarps > 0) {
       t.warp_prefix = split ? tt.d_prefix_light : tt.d_prefix;
       t.nq = split ? tt.d_nq_light : tt.d_nq;
@@ -872,7 +1038,7 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
       if (mine > 0x7fffffffLL) return fail(RCHEM_ERR_TOO_LARGE, "task exceeds the grid limit");
       CUDA_OK(fn(h->boys, mode, t, (unsigned)mine, pick_stream()));
       if (mine > 0) st.launches += 1;
-      account((split ? tt.nquartets_light : tt.nquartets) * (double)mine / (double)nblocks);
+      account(split ? tt.q_light_mine : tt.q_tensor_mine);
     }
     // --- block kernel (heavy bra pairs, J/K mode) ---
     if (split && tt.nblocks_heavy > 0) {
@@ -887,7 +1053,7 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
       if (mine > 0x7fffffffLL) return fail(RCHEM_ERR_TOO_LARGE, "task exceeds the grid limit");
       CUDA_OK(bfn(h->boys, t, (unsigned)mine, tt.smem_bytes, pick_stream()));
       if (mine > 0) st.launches += 1;
-      account((tt.nquartets - tt.nquartets_light) * (double)mine / (double)tt.nblocks_heavy);
+      account(tt.q_heavy_mine);
     }
   }
   // join: the main stream waits for every auxiliary stream
@@ -896,6 +1062,15 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
     CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_join[i], 0));
   }
   CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+  return RCHEM_OK;
+}
+
+// A build uses the handle's scratch buffers (Kh, packed J/D, light task tables).  When the
+// caller switched streams (rchem_set_stream) since the previous build, the new stream waits
+// for the old one's last use of them.
+int order_after_previous_build(rchem_basis* h) {
+  if (h->last_stream_valid && h->last_stream != h->stream)
+    CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_stream, 0));
   return RCHEM_OK;
 }
 
@@ -973,23 +1148,7 @@ int rchem_basis_create(int n, const double* origins, const int32_t* powers,
 
 void rchem_basis_destroy(rchem_basis* h) {
   if (!h) return;
-  if (h->ready) {
-    cudaSetDevice(h->device);
-    free_tasks(h);
-    for (Batch& bt : h->batches) {
-      cudaFree(bt.d_prim); cudaFree(bt.d_prim_far); cudaFree(bt.d_geom); cudaFree(bt.d_idx); cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
-    }
-    cudaFree(h->d_boys); cudaFree(h->d_delta_thr); cudaFree(h->d_delta_rows); cudaFree(h->d_D); cudaFree(h->d_Kh); cudaFree(h->d_JK); cudaFree(h->d_dmax); cudaFree(h->d_light_tasks); cudaFree(h->d_light_prefix); cudaFreeHost(h->h_light_tasks); cudaFreeHost(h->h_light_prefix);
-    cudaFree(h->d_fn_shell); cudaFree(h->d_pair_key); cudaFree(h->d_pair_fwd);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_light) cudaEventDestroy(h->ev_light);
-    for (int i = 0; i < rchem_basis::kAuxStreams; ++i) {
-      if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
-      if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
-    }
-  }
+  release_device_state(h);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -1076,6 +1235,16 @@ int rchem_set_option(rchem_basis* h, int key, double value) {
       if (value != 0.0 && value != 1.0) return fail(RCHEM_ERR_INVALID_ARG, "far_sched must be 0 or 1");
       h->far_sched = (int)value;
       return RCHEM_OK;
+    case RCHEM_OPT_SYMMETRIC_D_ONLY:
+      h->symmetric_only = value != 0.0;
+      return RCHEM_OK;
+    case RCHEM_OPT_LIGHT_KERNEL:
+      h->light_kernel = value != 0.0;
+      return RCHEM_OK;
+    case RCHEM_OPT_HEAVY_PASSES:
+      if (!(value >= 0.0)) return fail(RCHEM_ERR_INVALID_ARG, "heavy_passes must be >= 0");
+      h->heavy_passes = value;  // (the task tables are rebuilt by the next J/K build)
+      return RCHEM_OK;
   }
   return fail(RCHEM_ERR_INVALID_ARG, "unknown option");
 }
@@ -1088,6 +1257,9 @@ double rchem_get_option(const rchem_basis* h, int key) {
     case RCHEM_OPT_DEVICE: return h->device;
     case RCHEM_OPT_PRIM_EPS: return h->prim_eps;
     case RCHEM_OPT_FAR_SCHED: return h->far_sched;
+    case RCHEM_OPT_HEAVY_PASSES: return h->heavy_passes;
+    case RCHEM_OPT_LIGHT_KERNEL: return h->light_kernel;
+    case RCHEM_OPT_SYMMETRIC_D_ONLY: return h->symmetric_only;
   }
   return std::numeric_limits<double>::quiet_NaN();
 }
@@ -1109,6 +1281,7 @@ int rchem_use_own_stream(rchem_basis* h) {
 int rchem_get_stats(const rchem_basis* h, rchem_stats* out) {
   if (!h || !out) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
   *out = h->stats;
+  out->setup_ms = h->setup_ms;
   if (h->ready && h->ev0 && h->stats.launches > 0) {
     if (cudaEventSynchronize(h->ev1) == cudaSuccess) {
       float ms = 0.f;
@@ -1119,14 +1292,18 @@ int rchem_get_stats(const rchem_basis* h, rchem_stats* out) {
 }
 
 // ---------------- device-buffer entry points ---------------------------------------------
-int rchem_jk_direct_device(rchem_basis* h, const double* D_dev, double* JK_dev, int rank,
-                           int nranks) {
+// antisym = 0: J and K of a symmetric D are WRITTEN to JK_dev.
+// antisym = 1: D is antisymmetric; J is untouched (it vanishes) and K(D) is ADDED to JK_dev's K.
+static int jk_direct_device_impl(rchem_basis* h, const double* D_dev, double* JK_dev, int rank,
+                                 int nranks, int antisym) {
   if (!h || !D_dev || !JK_dev) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail(RCHEM_ERR_INVALID_ARG, "bad rank");
   int rc = ensure_ready(h);
   if (rc) return rc;
   CUDA_OK(cudaSetDevice(h->device));
   rc = ensure_tasks(h);
+  if (rc) return rc;
+  rc = order_after_previous_build(h);
   if (rc) return rc;
   const size_t nn = (size_t)h->N * h->N;
   const int N = h->N;
@@ -1148,13 +1325,24 @@ int rchem_jk_direct_device(rchem_basis* h, const double* D_dev, double* JK_dev, 
   proto.kbound = h->kbound;
   rc = run_tasks(h, kModeJK, proto, rank, nranks);
   if (rc) return rc;
-  for (const Batch& bt : h->batches)
-    finalize_j_kernel<<<(bt.npairs + 255) / 256, 256, 0, h->stream>>>(
-        bt.d_Jp, bt.d_idx, bt.npairs, bt.stride, ncart(bt.lb), bt.ncomp(), N, JK_dev);
-  finalize_k_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, h->stream>>>(h->d_Kh, JK_dev + nn, N);
+  if (!antisym)
+    for (const Batch& bt : h->batches)
+      finalize_j_kernel<<<(bt.npairs + 255) / 256, 256, 0, h->stream>>>(
+          bt.d_Jp, bt.d_idx, bt.npairs, bt.stride, ncart(bt.lb), bt.ncomp(), N, JK_dev);
+  finalize_k_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, h->stream>>>(
+      h->d_Kh, JK_dev + nn, N, antisym ? -1.0 : 1.0, antisym);
   CUDA_OK(cudaGetLastError());
-  h->stats.launches += 2 * (int)h->batches.size() + 2;  // pack_d, finalize_j per batch; absmax, finalize_k
+  // pack_d (+ finalize_j) per batch; absmax, finalize_k
+  h->stats.launches += (antisym ? 1 : 2) * (int)h->batches.size() + 2;
+  CUDA_OK(cudaEventRecord(h->ev_stream, h->stream));
+  h->last_stream = h->stream;
+  h->last_stream_valid = true;
   return RCHEM_OK;
+}
+
+int rchem_jk_direct_device(rchem_basis* h, const double* D_dev, double* JK_dev, int rank,
+                           int nranks) {
+  return jk_direct_device_impl(h, D_dev, JK_dev, rank, nranks, 0);
 }
 
 int rchem_build_I_device(rchem_basis* h, double* I_dev) {
@@ -1203,20 +1391,47 @@ int rchem_jk_direct(rchem_basis* h, const double* D, double* J, double* K) {
   if (!h || !D || !J || !K) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
   const int N = h->N;
   const size_t nn = (size_t)N * N;
-  double dmax = 0.0, amax = 0.0;
-  for (int i = 0; i < N; ++i)
-    for (int j = 0; j < i; ++j) {
-      dmax = std::max(dmax, std::fabs(D[(size_t)i * N + j]));
-      amax = std::max(amax, std::fabs(D[(size_t)i * N + j] - D[(size_t)j * N + i]));
-    }
-  if (amax > 1e-12 * std::max(dmax, 1e-300))
-    return fail(RCHEM_ERR_ASYMMETRIC_D, "JK_direct: the density matrix must be symmetric");
   int rc = ensure_ready(h);
   if (rc) return rc;
   CUDA_OK(cudaSetDevice(h->device));
-  CUDA_OK(cudaMemcpyAsync(h->d_D, D, nn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  rc = rchem_jk_direct_device(h, h->d_D, h->d_JK, 0, 1);
+  rc = order_after_previous_build(h);
   if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(h->d_D, D, nn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  // The digestion exploits D = D^T (what the reference's caller passes, rchem.rs:101-104).
+  // The reference itself accepts any D (basis.rs:383-428 uses no symmetry), so an asymmetric
+  // one is split on the device: J(D) = J(S) and K(D) = K(S) + K(A), S/A the symmetric /
+  // antisymmetric parts, K(A) antisymmetric -- a second build, only when it is needed.
+  CUDA_OK(cudaMemsetAsync(h->d_asym, 0, 2 * sizeof(double), h->stream));
+  asym_probe_kernel<<<148, 256, 0, h->stream>>>(h->d_D, N, reinterpret_cast<unsigned long long*>(h->d_asym));
+  double probe[2] = {0.0, 0.0};
+  CUDA_OK(cudaMemcpyAsync(probe, h->d_asym, sizeof(probe), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (probe[1] > 1e-14 * std::max(probe[0], 1e-300)) {
+    if (h->symmetric_only)
+      return fail(RCHEM_ERR_ASYMMETRIC_D, "JK_direct: the density matrix is not symmetric "
+                                          "(RCHEM_OPT_SYMMETRIC_D_ONLY is set)");
+    double *dS = nullptr, *dA = nullptr;
+    CUDA_OK(cudaMalloc(&dS, nn * sizeof(double)));
+    cudaError_t e = cudaMalloc(&dA, nn * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(dS); return fail(RCHEM_ERR_CUDA, cudaGetErrorString(e)); }
+    split_density_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, h->stream>>>(h->d_D, N, dS, dA);
+    rc = jk_direct_device_impl(h, dS, h->d_JK, 0, 1, 0);
+    rchem_stats first = h->stats;
+    if (rc == RCHEM_OK) rc = jk_direct_device_impl(h, dA, h->d_JK, 0, 1, 1);
+    if (rc == RCHEM_OK) {
+      h->stats.shell_quartets += first.shell_quartets;
+      h->stats.prim_quartets += first.prim_quartets;
+      h->stats.integrals += first.integrals;
+      h->stats.model_flops += first.model_flops;
+      h->stats.launches += first.launches;
+    }
+    cudaStreamSynchronize(h->stream);
+    cudaFree(dS); cudaFree(dA);
+    if (rc) return rc;
+  } else {
+    rc = rchem_jk_direct_device(h, h->d_D, h->d_JK, 0, 1);
+    if (rc) return rc;
+  }
   CUDA_OK(cudaMemcpyAsync(J, h->d_JK, nn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaMemcpyAsync(K, h->d_JK + nn, nn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -1280,7 +1495,7 @@ static int one_electron(rchem_basis* h, int which, int natoms, const double* ato
   if (rc) return rc;
   for (int c = 0; c < natoms && which == 2; ++c) Z.push_back((double)atomnos[c]);
   return one_electron_host(n, origins.data(), powers.data(), off.data(), exps.data(), coefs.data(),
-                           norms.data(), which, natoms, atomcoords, Z.data(), M);
+                           norms.data(), which, natoms, atomcoords, Z.data(), M, h->device);
 }
 
 int rchem_overlap(rchem_basis* h, double* S) { return one_electron(h, 0, 0, nullptr, nullptr, S); }

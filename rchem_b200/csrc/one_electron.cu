@@ -103,13 +103,13 @@ __device__ double prim_nuclear(double a1, double a2, const double* ra, const dou
 __global__ void one_electron_kernel(FlatBasisDev b, int which, int natoms,
                                     const double* __restrict__ atomcoords,
                                     const double* __restrict__ charges, double* __restrict__ M) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int n = b.n;
-  if (t >= n * (n + 1) / 2) return;
-  int mu = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  if (t >= (long long)n * (n + 1) / 2) return;
+  long long mu = (long long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
   while ((mu + 1) * (mu + 2) / 2 <= t) ++mu;
   while (mu * (mu + 1) / 2 > t) --mu;
-  const int nu = t - mu * (mu + 1) / 2;
+  const long long nu = t - mu * (mu + 1) / 2;
   const double* ra = b.origins + 3 * mu;
   const double* rb = b.origins + 3 * nu;
   const int* p1 = b.powers + 3 * mu;
@@ -136,10 +136,13 @@ __global__ void one_electron_kernel(FlatBasisDev b, int which, int natoms,
 // Host driver: flat CGTO arrays in, one N x N matrix out (host buffers).
 int one_electron_host(int n, const double* origins, const int* powers, const int* prim_offset,
                       const double* exps, const double* coefs, const double* norms, int which,
-                      int natoms, const double* atomcoords, const double* charges, double* M) {
+                      int natoms, const double* atomcoords, const double* charges, double* M,
+                      int device) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail_public(RCHEM_ERR_NO_DEVICE, "no CUDA device: librchem_b200 has no CPU path");
+  if (device < 0 || device >= ndev) return fail_public(RCHEM_ERR_INVALID_ARG, "bad device ordinal");
+  if (cudaSetDevice(device) != cudaSuccess) return fail_public(RCHEM_ERR_CUDA, "cudaSetDevice");
   for (int i = 0; i < n; ++i) {
     const int L = powers[3 * i] + powers[3 * i + 1] + powers[3 * i + 2];
     if (L > 4) return fail_public(RCHEM_ERR_UNSUPPORTED_AM, "one-electron kernels: l <= 4");
@@ -159,8 +162,8 @@ int one_electron_host(int n, const double* origins, const int* powers, const int
   if (e == cudaSuccess) e = cudaMalloc(&dM, (size_t)n * n * sizeof(double));
   if (e == cudaSuccess) {
     FlatBasisDev b{n, dO, dP, dF, dE, dC, dN};
-    const int npairs = n * (n + 1) / 2;
-    one_electron_kernel<<<(npairs + 63) / 64, 64>>>(b, which, natoms, dX, dZ, dM);
+    const long long npairs = (long long)n * (n + 1) / 2;
+    one_electron_kernel<<<(unsigned)((npairs + 63) / 64), 64>>>(b, which, natoms, dX, dZ, dM);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(M, dM, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost);

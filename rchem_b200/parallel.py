@@ -50,5 +50,10 @@ def allreduce_jk(jk_tensor, group=None):
 def jk_direct_distributed(basis, D_dev, JK_dev, rank, nranks, group=None):
     """This rank's share of JK_direct on device tensors (torch, float64, cuda), then the
     all-reduce.  D_dev: (N,N); JK_dev: (2,N,N) receives J and K."""
+    import torch
+
+    # the build and the collective must be ordered on ONE stream: torch's current stream (it
+    # produced D_dev, and NCCL's all-reduce is enqueued behind it)
+    basis.set_stream(torch.cuda.current_stream(D_dev.device).cuda_stream)
     basis.jk_direct_device(D_dev.data_ptr(), JK_dev.data_ptr(), rank, nranks)
     return allreduce_jk(JK_dev, group)

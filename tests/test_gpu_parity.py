@@ -136,13 +136,15 @@ def test_jk_inmem_fixture(rc):
     assert np.abs(J - g["J"]).max() < 1e-13 and np.abs(K - g["K"]).max() < 1e-13
 
 
-def test_asymmetric_density_is_rejected(rc, geo):
+def test_asymmetric_density_small(rc, orc, geo):
+    # basis.rs:383-428 accepts any D (details: test_gpu_kernels.py::test_asymmetric_density_...)
     z, x = geo.molecule(geo.WATER)
     b = rc.Basis.new(z, x, "STO-3G")
-    D = np.arange(49.0).reshape(7, 7)
-    with pytest.raises(rc.RchemError) as ei:
-        rc.JK_direct(np.zeros((7, 7)), np.zeros((7, 7)), b, D)
-    assert ei.value.code == -6
+    D = np.arange(49.0).reshape(7, 7) / 49.0
+    J, K = np.zeros((7, 7)), np.zeros((7, 7))
+    rc.JK_direct(J, K, b, D)
+    Jo, Ko = orc.jk_direct(orc.make_basis(z, x, "STO-3G"), D)
+    assert np.abs(J - Jo).max() < TOL and np.abs(K - Ko).max() < TOL
 
 
 # ---- screening: Schwarz bounds and the quartet list -----------------------------------------------

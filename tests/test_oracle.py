@@ -179,3 +179,43 @@ def test_one_electron_matrices_water(orc, geo):
     # Crawford's published core Hamiltonian elements for this geometry/basis
     H = T + V
     assert abs(H[0, 0] - (-32.5773954)) < 2e-6 and abs(H[1, 0] - (-7.5788328)) < 2e-6
+
+
+def test_sampled_parity_helper_equals_full_oracle_jk(orc, geo):
+    """oracle/parity.py (the checker of the BASELINE-size GPU tests and of bench.py's parity
+    block): element rows rebuilt under a Schwarz list equal the full oracle J/K when nothing is
+    screened, and drop exactly the screened quartets otherwise."""
+    from oracle import parity
+
+    z, x = geo.water_cluster(2)
+    ob = orc.make_basis(z, x, "STO-3G")
+    n = ob.n
+    D = geo.synthetic_density(n)
+    I = orc.build_I(ob)
+    J, K = orc.jk_inmem(I, D)
+    l = np.array([0, 0, 1, 0, 0] * 2, dtype=np.int32)
+    first = np.array([0, 1, 2, 5, 6, 7, 8, 9, 12, 13], dtype=np.int32)
+    ns = len(l)
+    ii, jj = np.tril_indices(ns)
+    swap = l[ii] < l[jj]
+    sa, sb = np.where(swap, jj, ii), np.where(swap, ii, jj)
+    ncart = lambda m: (m + 1) * (m + 2) // 2
+    Q = np.array([np.sqrt(max(abs(I[first[a] + i, first[b] + j, first[a] + i, first[b] + j])
+                              for i in range(ncart(l[a])) for j in range(ncart(l[b]))))
+                  for a, b in zip(sa, sb)])
+    fn_shell, Qm = parity.shell_maps(l, first, sa, sb, Q)
+    assert list(fn_shell[:7]) == [0, 1, 2, 2, 2, 3, 4] and np.array_equal(Qm, Qm.T)
+    els = parity.pick_elements(l, first, sa, sb, Q, 10)
+    assert len(els) == 10 and els == parity.pick_elements(l, first, sa, sb, Q, 10)
+    Jr, Kr = parity.jk_elements(orc, ob, D, els, fn_shell, Qm, 0.0)
+    mu, nu = np.array(els).T
+    assert np.abs(Jr - J[mu, nu]).max() < 1e-13 and np.abs(Kr - K[mu, nu]).max() < 1e-13
+    # with screening: identical to masking the tensor by the same rule
+    tau = 1e-3
+    Qf = Qm[np.ix_(fn_shell, fn_shell)]
+    mask = Qf[:, :, None, None] * Qf[None, None, :, :] >= tau
+    Js = np.einsum("mnls,ls->mn", I * mask, D)
+    Ks = np.einsum("mlns,ls->mn", I * mask, D)
+    Jr, Kr = parity.jk_elements(orc, ob, D, els, fn_shell, Qm, tau)
+    assert np.abs(Jr - Js[mu, nu]).max() < 1e-13 and np.abs(Kr - Ks[mu, nu]).max() < 1e-13
+    assert np.abs(Js - J).max() > 1e-6  # (the screening removed something)
