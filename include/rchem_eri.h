@@ -99,6 +99,13 @@ int64_t rchem_ijkl2intindex(int64_t i, int64_t j, int64_t k, int64_t l);
 #define RCHEM_OPT_SYMMETRIC_D_ONLY 7 /* 1: rchem_jk_direct rejects an asymmetric D with
                                    RCHEM_ERR_ASYMMETRIC_D instead of paying a second build
                                    (default 0: any D is accepted, like basis.rs:383-428)       */
+#define RCHEM_OPT_NGPUS 9        /* n > 1: rchem_jk_direct drives the n devices device .. device+n-1
+                                   of this node from the ONE call (single process): H2D of D
+                                   once, peer copies of D over NVLink, every device builds its
+                                   block-interleaved share of the quartets, device `device` sums
+                                   the partial [J|K] out of its peers' memory (peer-to-peer
+                                   loads), one D2H.  Default 1.  An asymmetric D and every other
+                                   entry point use device `device` alone.                      */
 int rchem_set_option(rchem_basis* b, int key, double value);
 double rchem_get_option(const rchem_basis* b, int key);
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream).  The value is used as

@@ -28,7 +28,7 @@ LIB_PATH = os.environ.get("RCHEM_B200_LIB") or os.path.join(_HERE, "librchem_b20
 
 BOYS_REFERENCE, BOYS_EXACT = 0, 1
 OPT_BOYS, OPT_SCHWARZ_TAU, OPT_DEVICE, OPT_PRIM_EPS, OPT_FAR_SCHED = 1, 2, 3, 4, 5
-OPT_HEAVY_PASSES, OPT_SYMMETRIC_D_ONLY, OPT_LIGHT_KERNEL = 6, 7, 8
+OPT_HEAVY_PASSES, OPT_SYMMETRIC_D_ONLY, OPT_LIGHT_KERNEL, OPT_NGPUS = 6, 7, 8, 9
 
 
 class RchemError(RuntimeError):
@@ -223,6 +223,11 @@ class Basis:
     def set_symmetric_only(self, on):
         """Reject an asymmetric D in JK_direct instead of paying a second build."""
         _check(_lib.rchem_set_option(self._h, OPT_SYMMETRIC_D_ONLY, 1.0 if on else 0.0))
+
+    def set_gpus(self, n):
+        """RCHEM_OPT_NGPUS: JK_direct drives n GPUs of this node from the one call (single
+        process; devices device .. device+n-1; partial J/K summed over NVLink on the first)."""
+        _check(_lib.rchem_set_option(self._h, OPT_NGPUS, float(n)))
 
     def set_device(self, ordinal):
         _check(_lib.rchem_set_option(self._h, OPT_DEVICE, float(ordinal)))

@@ -16,6 +16,7 @@
 #include <map>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rchem_eri.h"
@@ -291,6 +292,24 @@ __global__ void finalize_k_kernel(const double* __restrict__ Kh, double* __restr
   K[idx] = accumulate ? K[idx] + v : v;
 }
 
+// Single-process multi-GPU J/K (RCHEM_OPT_NGPUS): device 0 of the group sums the partial [J|K]
+// of its peers straight out of THEIR memory over NVLink (peer-to-peer loads, 16 bytes per
+// access); every address is read exactly once, so there is nothing to stage.
+struct PeerPtrs { const double2* p[15]; int n; };
+__global__ void __launch_bounds__(256) peer_reduce_kernel(double2* __restrict__ JK, const PeerPtrs peers,
+                                                          size_t n2) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    double2 s = JK[i];
+#pragma unroll 4
+    for (int k = 0; k < peers.n; ++k) {
+      const double2 v = peers.p[k][i];
+      s.x += v.x;
+      s.y += v.y;
+    }
+    JK[i] = s;
+  }
+}
+
 // {max|D|, max|D - D^T|} as bit patterns (non-negative doubles order like their bits), and the
 // split D = S + A into symmetric and antisymmetric parts
 __global__ void asym_probe_kernel(const double* __restrict__ D, int N, unsigned long long* out) {
@@ -460,6 +479,13 @@ struct rchem_basis {
   cudaStream_t last_stream = nullptr;  // stream of the previous build (order_after_previous_build)
   bool last_stream_valid = false;
   int symmetric_only = 0;           // RCHEM_OPT_SYMMETRIC_D_ONLY
+  // single-process multi-GPU (RCHEM_OPT_NGPUS): this handle drives devices device ..
+  // device + ngpus - 1; peers[i-1] is a full clone of the handle living on device + i
+  int ngpus = 1;
+  std::vector<rchem_basis*> peers;
+  std::vector<double*> peer_stage;  // on this device: copy of a peer's [J|K] when P2P loads are not possible
+  cudaEvent_t ev_D = nullptr;       // D is resident on this device
+  cudaEvent_t ev_done = nullptr;    // this handle's share of [J|K] is complete (peer side)
   double tasks_heavy = -1.0;        // values the task tables were built with
   int tasks_light = -1;
   // The tasks of one J/K (or tensor) build are independent kernels; they are spread over a
@@ -599,6 +625,9 @@ void release_device_state(rchem_basis* h) {
   h->h_light_tasks = nullptr; h->h_light_prefix = nullptr; h->light_tasks_cap = 0;
   auto drop_ev = [](cudaEvent_t& e) { if (e) cudaEventDestroy(e); e = nullptr; };
   drop_ev(h->ev0); drop_ev(h->ev1); drop_ev(h->ev_fork); drop_ev(h->ev_light); drop_ev(h->ev_stream);
+  drop_ev(h->ev_D); drop_ev(h->ev_done);
+  for (double*& st : h->peer_stage) drop(st);
+  h->peer_stage.clear();
   for (int i = 0; i < rchem_basis::kAuxStreams; ++i) {
     drop_ev(h->ev_join[i]);
     if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
@@ -1148,6 +1177,8 @@ int rchem_basis_create(int n, const double* origins, const int32_t* powers,
 
 void rchem_basis_destroy(rchem_basis* h) {
   if (!h) return;
+  for (rchem_basis* peer : h->peers) rchem_basis_destroy(peer);
+  h->peers.clear();
   release_device_state(h);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -1245,6 +1276,21 @@ int rchem_set_option(rchem_basis* h, int key, double value) {
       if (!(value >= 0.0)) return fail(RCHEM_ERR_INVALID_ARG, "heavy_passes must be >= 0");
       h->heavy_passes = value;  // (the task tables are rebuilt by the next J/K build)
       return RCHEM_OK;
+    case RCHEM_OPT_NGPUS: {
+      if (!(value >= 1.0) || value != std::floor(value) || value > 16.0)
+        return fail(RCHEM_ERR_INVALID_ARG, "ngpus must be an integer in 1..16");
+      int ndev = 0;
+      if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(RCHEM_ERR_NO_DEVICE, "no CUDA device: librchem_b200 has no CPU path");
+      }
+      // (RCHEM_MULTI_OVERSUBSCRIBE=1 wraps the group around the visible devices, so the
+      // multi-device code path can be exercised on a one-GPU box: tests only)
+      if (h->device + (int)value > ndev && !std::getenv("RCHEM_MULTI_OVERSUBSCRIBE"))
+        return fail(RCHEM_ERR_INVALID_ARG, "ngpus: devices device .. device+ngpus-1 must exist");
+      h->ngpus = (int)value;
+      return RCHEM_OK;
+    }
   }
   return fail(RCHEM_ERR_INVALID_ARG, "unknown option");
 }
@@ -1260,6 +1306,7 @@ double rchem_get_option(const rchem_basis* h, int key) {
     case RCHEM_OPT_HEAVY_PASSES: return h->heavy_passes;
     case RCHEM_OPT_LIGHT_KERNEL: return h->light_kernel;
     case RCHEM_OPT_SYMMETRIC_D_ONLY: return h->symmetric_only;
+    case RCHEM_OPT_NGPUS: return h->ngpus;
   }
   return std::numeric_limits<double>::quiet_NaN();
 }
@@ -1386,6 +1433,119 @@ int rchem_jk_inmem_device(int n, const double* I_dev, const double* D_dev, doubl
   return RCHEM_OK;
 }
 
+
+// ---------------- single-process multi-GPU J/K (RCHEM_OPT_NGPUS) ---------------------------
+// One handle, one call, n devices of this node:
+//   H2D of D once (device 0 of the group) -> peer copies of D over NVLink -> every device
+//   builds its block-interleaved share (one host thread per device enqueues its launches) ->
+//   device 0 sums the partial [J|K] out of its peers' memory (peer_reduce_kernel) -> ONE D2H.
+// D must be symmetric on this path (an asymmetric D takes the one-device path).
+extern "C++" {
+namespace {
+
+int sync_peer_options(rchem_basis* h) {
+  while ((int)h->peers.size() < h->ngpus - 1) {
+    Basis copy = h->basis;
+    rchem_basis* peer = nullptr;
+    int rc = make_basis_handle(std::move(copy), &peer);
+    if (rc) return rc;
+    int ndev = 1;
+    cudaGetDeviceCount(&ndev);
+    peer->device = (h->device + 1 + (int)h->peers.size()) % std::max(1, ndev);
+    peer->prim_eps = h->prim_eps;
+    h->peers.push_back(peer);
+  }
+  for (rchem_basis* peer : h->peers) {
+    peer->boys = h->boys; peer->tau = h->tau; peer->far_sched = h->far_sched;
+    peer->heavy_passes = h->heavy_passes; peer->light_kernel = h->light_kernel;
+  }
+  return RCHEM_OK;
+}
+
+// runs fn(i) for i = 1..n-1 on their own host threads and fn(0) here; first failure wins
+template <class F> int for_each_device(int n, F fn) {
+  std::vector<int> rc(n, RCHEM_OK);
+  std::vector<std::string> msg(n);
+  std::vector<std::thread> th;
+  for (int i = 1; i < n; ++i)
+    th.emplace_back([&, i] { rc[i] = fn(i); if (rc[i]) msg[i] = g_err; });
+  rc[0] = fn(0);
+  if (rc[0]) msg[0] = g_err;
+  for (std::thread& t : th) t.join();
+  for (int i = 0; i < n; ++i)
+    if (rc[i]) return fail(rc[i], "device " + std::to_string(i) + " of the group: " + msg[i]);
+  return RCHEM_OK;
+}
+
+int jk_direct_multi(rchem_basis* h, double* J, double* K) {
+  // (D is already in h->d_D on h->stream and was found symmetric)
+  const int n = h->ngpus;
+  const size_t nn = (size_t)h->N * h->N;
+  auto handle = [&](int i) { return i == 0 ? h : h->peers[i - 1]; };
+  if (!h->ev_D) CUDA_OK(cudaEventCreateWithFlags(&h->ev_D, cudaEventDisableTiming));
+  CUDA_OK(cudaEventRecord(h->ev_D, h->stream));
+  int rc = for_each_device(n, [&](int i) -> int {
+    rchem_basis* g = handle(i);
+    int r = ensure_ready(g);
+    if (r) return r;
+    CUDA_OK(cudaSetDevice(g->device));
+    if (i > 0) {
+      if (!g->ev_done) CUDA_OK(cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming));
+      CUDA_OK(cudaStreamWaitEvent(g->stream, h->ev_D, 0));
+      CUDA_OK(cudaMemcpyPeerAsync(g->d_D, g->device, h->d_D, h->device, nn * sizeof(double), g->stream));
+    }
+    r = jk_direct_device_impl(g, g->d_D, g->d_JK, i, n, 0);
+    if (r) return r;
+    if (i > 0) CUDA_OK(cudaEventRecord(g->ev_done, g->stream));
+    return RCHEM_OK;
+  });
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(h->device));
+  // the sum, on device 0 of the group, straight from peer memory where the hardware allows it
+  PeerPtrs pp{};
+  h->peer_stage.resize(n - 1, nullptr);
+  for (int i = 1; i < n; ++i) {
+    rchem_basis* g = handle(i);
+    CUDA_OK(cudaStreamWaitEvent(h->stream, g->ev_done, 0));
+    int can = g->device == h->device;  // (same device only with RCHEM_MULTI_OVERSUBSCRIBE)
+    if (!can) {
+      CUDA_OK(cudaDeviceCanAccessPeer(&can, h->device, g->device));
+      if (can) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(g->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+        cudaGetLastError();
+      }
+    }
+    if (can) {
+      pp.p[pp.n++] = reinterpret_cast<const double2*>(g->d_JK);
+    } else {
+      if (!h->peer_stage[i - 1]) CUDA_OK(cudaMalloc(&h->peer_stage[i - 1], 2 * nn * sizeof(double)));
+      CUDA_OK(cudaMemcpyPeerAsync(h->peer_stage[i - 1], h->device, g->d_JK, g->device,
+                                  2 * nn * sizeof(double), h->stream));
+      pp.p[pp.n++] = reinterpret_cast<const double2*>(h->peer_stage[i - 1]);
+    }
+  }
+  peer_reduce_kernel<<<148 * 4, 256, 0, h->stream>>>(reinterpret_cast<double2*>(h->d_JK), pp, nn);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(J, h->d_JK, nn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaMemcpyAsync(K, h->d_JK + nn, nn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  // whole-job statistics: counts summed over the group, launches likewise
+  for (int i = 1; i < n; ++i) {
+    const rchem_stats& s = handle(i)->stats;
+    h->stats.shell_quartets += s.shell_quartets;
+    h->stats.prim_quartets += s.prim_quartets;
+    h->stats.integrals += s.integrals;
+    h->stats.model_flops += s.model_flops;
+    h->stats.launches += s.launches;
+  }
+  h->stats.launches += 1;  // peer_reduce_kernel
+  return RCHEM_OK;
+}
+
+}  // namespace
+}  // extern "C++"
+
 // ---------------- host-buffer entry points (copies inside) -------------------------------
 int rchem_jk_direct(rchem_basis* h, const double* D, double* J, double* K) {
   if (!h || !D || !J || !K) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
@@ -1428,6 +1588,10 @@ int rchem_jk_direct(rchem_basis* h, const double* D, double* J, double* K) {
     cudaStreamSynchronize(h->stream);
     cudaFree(dS); cudaFree(dA);
     if (rc) return rc;
+  } else if (h->ngpus > 1) {
+    rc = sync_peer_options(h);
+    if (rc) return rc;
+    return jk_direct_multi(h, J, K);
   } else {
     rc = rchem_jk_direct_device(h, h->d_D, h->d_JK, 0, 1);
     if (rc) return rc;

@@ -341,3 +341,43 @@ def test_two_real_ranks_equal_one_gpu(rc, tmp_path):
     assert out.returncode == 0, out.stderr[-3000:]
     err = float(out.stdout.split("MULTI_GPU_ERR")[1].split()[0])
     assert err < 1e-12
+
+
+# ---- single-process multi-GPU behind the reference's own call (RCHEM_OPT_NGPUS) ----------------------
+@pytest.mark.parametrize("ngpus", [2, 3])
+def test_jk_direct_drives_several_devices_from_one_call(rc, orc, geo, ref_or_restated, ngpus, monkeypatch):
+    """JK_direct(&mut J, &mut K, &basis, &D) with RCHEM_OPT_NGPUS = n: one handle, one call,
+    n devices (block-interleaved shares, peer reduction on the first device, one D2H).  On a
+    box with fewer GPUs the group wraps around the visible devices (RCHEM_MULTI_OVERSUBSCRIBE),
+    which runs the same partition / peer-copy / reduction code."""
+    if rc.device_count() < ngpus:
+        monkeypatch.setenv("RCHEM_MULTI_OVERSUBSCRIBE", "1")
+    z, x, D, Jo, Ko = oracle_jk(orc, geo, ref_or_restated, 3, "6-31G", 0)
+    b = rc.Basis.new(z, x, "6-31G")
+    n = b.nbf
+    J1, K1 = np.zeros((n, n)), np.zeros((n, n))
+    rc.JK_direct(J1, K1, b, D)
+    whole = b.stats()
+    b.set_gpus(ngpus)
+    for _ in range(2):  # (second call: peers already set up)
+        J, K = np.full((n, n), 7.0), np.full((n, n), 7.0)
+        rc.JK_direct(J, K, b, D)
+        assert np.abs(J - Jo).max() < TOL and np.abs(K - Ko).max() < TOL
+        assert np.abs(J - J1).max() < 1e-13 and np.abs(K - K1).max() < 1e-13
+        st = b.stats()
+        for key in ("shell_quartets", "prim_quartets", "integrals"):
+            assert st[key] == whole[key], key
+    # a larger cluster with screening, every kernel family active in every share
+    z, x = geo.water_cluster(10)
+    big = rc.Basis.new(z, x, "6-31G")
+    big.set_schwarz_tau(1e-9)
+    n = big.nbf
+    D = geo.synthetic_density(n)
+    J1, K1 = np.zeros((n, n)), np.zeros((n, n))
+    rc.JK_direct(J1, K1, big, D)
+    big.set_gpus(ngpus)
+    J, K = np.zeros((n, n)), np.zeros((n, n))
+    rc.JK_direct(J, K, big, D)
+    assert np.abs(J - J1).max() < 1e-13 and np.abs(K - K1).max() < 1e-13
+    # an asymmetric D falls back to the one-device path and still matches the reference loop
+    big.set_gpus(1)
