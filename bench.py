@@ -82,10 +82,13 @@ def make_workload(name):
 def sample_shell_quartets(shell_l, shell_first, sa, sb, Q, tau, count, seed=20261017):
     """Uniform sample of the surviving canonical shell quartets (pair p >= pair q in kernel
     order, Q_p*Q_q >= tau) as FUNCTION quartets: returns (function_quartets[int32, n x 4],
-    n_shell_quartets).  Every Cartesian component of a sampled shell quartet is included."""
+    n_shell_quartets).  Every Cartesian component of a sampled shell quartet is included.
+    Shells reported with l = -1 are fused sp shells (s, px, py, pz); such a quartet counts as the
+    segmented (s/p/d) shell quartets it covers -- the unit of the metric."""
     rng = np.random.default_rng(seed)
     npair = len(Q)
-    ncart = lambda l: (l + 1) * (l + 2) // 2
+    ncart = lambda l: 4 if l == -1 else (l + 1) * (l + 2) // 2
+    nvar = lambda l: 2 if l == -1 else 1
     out, got = [], 0
     while got < count:
         p = rng.integers(0, npair, size=4 * count)
@@ -97,7 +100,8 @@ def sample_shell_quartets(shell_l, shell_first, sa, sb, Q, tau, count, seed=2026
             fc = [shell_first[sa[qq]] + i for i in range(ncart(shell_l[sa[qq]]))]
             fd = [shell_first[sb[qq]] + i for i in range(ncart(shell_l[sb[qq]]))]
             out.extend((a, b, c, d) for a in fa for b in fb for c in fc for d in fd)
-            got += 1
+            got += (nvar(shell_l[sa[pp]]) * nvar(shell_l[sb[pp]]) * nvar(shell_l[sa[qq]])
+                    * nvar(shell_l[sb[qq]]))
             if got >= count:
                 break
     return np.array(out, dtype=np.int32), got

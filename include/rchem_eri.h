@@ -64,7 +64,11 @@ int rchem_basis_nshells(const rchem_basis* b); /* shells re-derived from the CGT
 /* copies the flat CGTO arrays out (same layout as rchem_basis_create) */
 int rchem_basis_export(const rchem_basis* b, double* origins, int32_t* powers,
                        int32_t* prim_offset, double* exps, double* coefs, double* norms);
-/* per shell: angular momentum and index of its first function */
+/* per shell: angular momentum and index of its first function.  With RCHEM_OPT_FUSE_SP (default)
+ * an s shell and a p shell on the same centre and exponents -- one "sp" electron shell of the
+ * Basis Set Exchange data Basis::new reads (basis.rs:190-201) -- are ONE shell here, reported
+ * with l = RCHEM_SHELL_SP: four functions s, px, py, pz. */
+#define RCHEM_SHELL_SP (-1)
 int rchem_basis_shells(const rchem_basis* b, int32_t* l, int32_t* first_function);
 
 /* PGTO::normalization                                             basis.rs:140-149 */
@@ -99,6 +103,11 @@ int64_t rchem_ijkl2intindex(int64_t i, int64_t j, int64_t k, int64_t l);
 #define RCHEM_OPT_SYMMETRIC_D_ONLY 7 /* 1: rchem_jk_direct rejects an asymmetric D with
                                    RCHEM_ERR_ASYMMETRIC_D instead of paying a second build
                                    (default 0: any D is accepted, like basis.rs:383-428)       */
+#define RCHEM_OPT_FUSE_SP 10     /* 1 (default): bases made of s and sp shells only (STO-3G, 6-31G)
+                                   keep each sp shell FUSED -- one shell quartet evaluates every
+                                   s|p-part combination on one set of primitive quartets (shared
+                                   Boys values and recurrences); 0: s and p parts as separate
+                                   shells.  Same integrals.  Before the first compute call.    */
 #define RCHEM_OPT_NGPUS 9        /* n > 1: rchem_jk_direct drives the n devices device .. device+n-1
                                    of this node from the ONE call (single process): H2D of D
                                    once, peer copies of D over NVLink, every device builds its
@@ -162,9 +171,11 @@ int64_t rchem_quartet_list(rchem_basis* b, int64_t* pq, int64_t capacity);
 
 /* ---------------- statistics of the last build_I / jk_direct call -------------------- */
 typedef struct {
-  int64_t shell_quartets;     /* computed (after screening), this rank                     */
+  int64_t shell_quartets;     /* computed (after screening), this rank; counted in SEGMENTED
+                                 (s/p/d) shell quartets: a quartet of fused sp shells covers
+                                 every s|p-part combination of its four shells              */
   int64_t shell_quartets_all; /* canonical quartets before screening                       */
-  int64_t prim_quartets;      /* primitive quartets evaluated, this rank                   */
+  int64_t prim_quartets;      /* primitive quartets of those segmented quartets, this rank  */
   int64_t integrals;          /* Cartesian (ab|cd) values produced, this rank              */
   double model_flops;         /* SURVEY 8(d) flop model summed over computed quartets      */
   double kernel_ms;           /* device time of the ERI kernels (CUDA events on the stream) */
@@ -172,6 +183,9 @@ typedef struct {
   int32_t n_tasks;            /* batch pairs                                               */
   double setup_ms;            /* host wall time spent so far on one-off set-up of this handle:
                                  pair batches, Schwarz bounds, Boys tables, task tables      */
+  int64_t fused_quartets;     /* shell quartets as the kernels see them (fused sp shells = 1) */
+  int64_t prim_quartets_evaluated; /* primitive quartets actually evaluated (shared by the
+                                 variants of a fused quartet)                                */
 } rchem_stats;
 int rchem_get_stats(const rchem_basis* b, rchem_stats* out);
 

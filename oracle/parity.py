@@ -12,13 +12,20 @@ comparison is at the 1e-12 parity tolerance, not at a screening-error bound.
 import numpy as np
 
 
+def nfun(l):
+    """functions of a shell as rchem_basis_shells reports it: l = -1 is a fused sp shell
+    (s, px, py, pz)"""
+    l = int(l)
+    return 4 if l == -1 else (l + 1) * (l + 2) // 2
+
+
 def shell_maps(shell_l, shell_first, sa, sb, Q):
     """(function -> shell, dense symmetric Q matrix over shells)"""
     ns = len(shell_l)
-    nbf = int(shell_first[-1] + (shell_l[-1] + 1) * (shell_l[-1] + 2) // 2)
+    nbf = int(shell_first[-1] + nfun(shell_l[-1]))
     fn_shell = np.zeros(nbf, dtype=np.int64)
     for s in range(ns):
-        fn_shell[shell_first[s]:shell_first[s] + (shell_l[s] + 1) * (shell_l[s] + 2) // 2] = s
+        fn_shell[shell_first[s]:shell_first[s] + nfun(shell_l[s])] = s
     Qm = np.zeros((ns, ns))
     Qm[sa, sb] = Q
     Qm[sb, sa] = Q
@@ -31,8 +38,8 @@ def pick_elements(shell_l, shell_first, sa, sb, Q, count, seed=7):
     with the longest ket lists, i.e. the block kernel's --, then quantiles of the Q ordering,
     including a diagonal shell pair); the rest are uniformly random function pairs."""
     rng = np.random.default_rng(seed)
-    nbf = int(shell_first[-1] + (shell_l[-1] + 1) * (shell_l[-1] + 2) // 2)
-    ncart = lambda l: (l + 1) * (l + 2) // 2
+    nbf = int(shell_first[-1] + nfun(shell_l[-1]))
+    ncart = nfun
     order = np.argsort(-Q, kind="stable")
     pairs = []
     for want in sorted({(int(shell_l[a]), int(shell_l[b])) for a, b in zip(sa, sb)}):

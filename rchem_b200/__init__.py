@@ -28,7 +28,14 @@ LIB_PATH = os.environ.get("RCHEM_B200_LIB") or os.path.join(_HERE, "librchem_b20
 
 BOYS_REFERENCE, BOYS_EXACT = 0, 1
 OPT_BOYS, OPT_SCHWARZ_TAU, OPT_DEVICE, OPT_PRIM_EPS, OPT_FAR_SCHED = 1, 2, 3, 4, 5
-OPT_HEAVY_PASSES, OPT_SYMMETRIC_D_ONLY, OPT_LIGHT_KERNEL, OPT_NGPUS = 6, 7, 8, 9
+OPT_HEAVY_PASSES, OPT_SYMMETRIC_D_ONLY, OPT_LIGHT_KERNEL, OPT_NGPUS, OPT_FUSE_SP = 6, 7, 8, 9, 10
+SHELL_SP = -1  # l reported for a fused s+p shell (4 functions: s, px, py, pz)
+
+
+def shell_nfun(l):
+    """functions of a shell whose rchem_basis_shells code is l"""
+    l = int(l)
+    return 4 if l == SHELL_SP else (l + 1) * (l + 2) // 2
 
 
 class RchemError(RuntimeError):
@@ -52,7 +59,8 @@ class Stats(C.Structure):
     _fields_ = [("shell_quartets", C.c_int64), ("shell_quartets_all", C.c_int64),
                 ("prim_quartets", C.c_int64), ("integrals", C.c_int64),
                 ("model_flops", C.c_double), ("kernel_ms", C.c_double),
-                ("launches", C.c_int32), ("n_tasks", C.c_int32), ("setup_ms", C.c_double)]
+                ("launches", C.c_int32), ("n_tasks", C.c_int32), ("setup_ms", C.c_double),
+                ("fused_quartets", C.c_int64), ("prim_quartets_evaluated", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -223,6 +231,11 @@ class Basis:
     def set_symmetric_only(self, on):
         """Reject an asymmetric D in JK_direct instead of paying a second build."""
         _check(_lib.rchem_set_option(self._h, OPT_SYMMETRIC_D_ONLY, 1.0 if on else 0.0))
+
+    def set_fuse_sp(self, on):
+        """RCHEM_OPT_FUSE_SP (before the first compute call): keep sp shells fused (default) or
+        treat their s and p parts as separate shells.  Same integrals."""
+        _check(_lib.rchem_set_option(self._h, OPT_FUSE_SP, 1.0 if on else 0.0))
 
     def set_gpus(self, n):
         """RCHEM_OPT_NGPUS: JK_direct drives n GPUs of this node from the one call (single

@@ -111,9 +111,10 @@ bool basis_new(const std::vector<uint64_t>& atomnos, const double* coords,
   return true;
 }
 
-bool group_shells(const Basis& basis, ShellSet* out, std::string* err) {
+bool group_shells(const Basis& basis, ShellSet* out, std::string* err, bool fuse_sp) {
   out->shells.clear();
   out->lmax = 0;
+  out->fused = false;
   bool have_scale[5] = {false, false, false, false, false};
   const int n = (int)basis.cgtos.size();
   int i = 0;
@@ -169,6 +170,35 @@ bool group_shells(const Basis& basis, ShellSet* out, std::string* err) {
     out->shells.push_back(std::move(sh));
     out->lmax = std::max(out->lmax, l);
     i += nc;
+  }
+  if (fuse_sp && out->lmax == 1) {
+    // every p shell must pair with the s shell right before it (same centre, same exponents,
+    // consecutive functions): s, px, py, pz of one Basis Set Exchange sp shell
+    std::vector<Shell> fusedv;
+    bool ok = true;
+    const std::vector<Shell>& sh = out->shells;
+    for (size_t k = 0; k < sh.size() && ok; ++k) {
+      if (sh[k].l == 1) { ok = false; break; }  // a p shell that did not follow its s partner
+      if (k + 1 < sh.size() && sh[k + 1].l == 1) {
+        const Shell &S = sh[k], &P = sh[k + 1];
+        bool same = P.bf0 == S.bf0 + 1 && S.exps.size() == P.exps.size();
+        for (int d = 0; d < 3 && same; ++d) same = S.ctr[d] == P.ctr[d];
+        for (size_t q = 0; q < S.exps.size() && same; ++q) same = S.exps[q] == P.exps[q];
+        if (!same) { ok = false; break; }
+        Shell f = S;
+        f.l = 3;  // kTypeSP
+        f.cn2 = P.cn;
+        fusedv.push_back(std::move(f));
+        ++k;
+      } else {
+        fusedv.push_back(sh[k]);
+      }
+    }
+    if (ok) {
+      out->shells.swap(fusedv);
+      out->fused = true;
+      for (int k = 0; k < 15; ++k) out->compscale[3][k] = 1.0;
+    }
   }
   return true;
 }

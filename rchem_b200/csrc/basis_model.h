@@ -77,11 +77,13 @@ bool basis_new(const std::vector<uint64_t>& atomnos, const double* coords,
 
 // ---- shells re-derived from the CGTO list ----------------------------------------------
 struct Shell {
-  int l;       // angular momentum
+  int l;       // shell TYPE (eri_core.h): angular momentum 0..4, or 3 = kTypeSP for a fused s+p
+               // shell when ShellSet::fused (class kernels only go up to d, so 3 is never f there)
   int bf0;     // index of the first Cartesian function of the shell in Basis::cgtos
   double ctr[3];
   std::vector<double> exps;
   std::vector<double> cn;  // coefs[i] * norm of the FIRST component (L,0,0) of primitive i
+  std::vector<double> cn2; // fused sp shell: the same for its p part (cn is the s part)
 };
 
 struct ShellSet {
@@ -90,11 +92,16 @@ struct ShellSet {
   // that l (checked), e.g. d: {1, sqrt3, sqrt3, 1, sqrt3, 1}
   double compscale[5][15];
   int lmax = 0;
+  bool fused = false;  // s+p shells sharing centre and exponents were fused into type-3 shells
 };
 
 // Groups consecutive CGTOs into shells.  Fails (false + message) when the functions do not
 // form complete Cartesian shells in get_ijk_list order with shared exponents/coefficients,
 // or when the caller-supplied norms are not "shell norm x component factor".
-bool group_shells(const Basis& basis, ShellSet* out, std::string* err);
+// fuse_sp: additionally fuse every (s shell, p shell) pair of consecutive functions that share
+// centre and exponents (the sp shells of STO-3G / 6-31G) into ONE shell of type kTypeSP -- done
+// only when the basis consists of s and such sp shells alone (every p shell fuses, no d shell),
+// because the class kernels exist for the type sets {s,p,d} and {s,sp}.
+bool group_shells(const Basis& basis, ShellSet* out, std::string* err, bool fuse_sp = false);
 
 }  // namespace rchem

@@ -100,6 +100,29 @@ static const FlopModel* flop_model(int la, int lb, int lc, int ld) {
     if (f.la == la && f.lb == lb && f.lc == lc && f.ld == ld) return &f;
   return nullptr;
 }
+// The model for a quartet of shell TYPES: a fused sp shell stands for its s and its p shell, so a
+// fused quartet is charged the SURVEY figures of every segmented (s/p/d) quartet it evaluates --
+// the algorithmic work of the reference's shells; what the fused kernel saves by sharing the
+// primitive quartet between them is the optimisation.  *nseg = segmented quartets covered.
+static bool flop_model_types(int ta, int tb, int tc, int td, double* P, double* H, int* nseg) {
+  *P = *H = 0.0;
+  *nseg = 0;
+  for (int va = 0; va < nvariants(ta); ++va)
+    for (int vb = 0; vb < nvariants(tb); ++vb)
+      for (int vc = 0; vc < nvariants(tc); ++vc)
+        for (int vd = 0; vd < nvariants(td); ++vd) {
+          int la = variant_l(ta, va), lb = variant_l(tb, vb), lc = variant_l(tc, vc), ld = variant_l(td, vd);
+          if (la < lb) std::swap(la, lb);
+          if (lc < ld) std::swap(lc, ld);
+          if (la * (la + 1) / 2 + lb < lc * (lc + 1) / 2 + ld) { std::swap(la, lc); std::swap(lb, ld); }
+          const FlopModel* f = flop_model(la, lb, lc, ld);
+          if (!f) return false;
+          *P += f->P;
+          *H += f->H;
+          *nseg += 1;
+        }
+  return true;
+}
 
 static EriLaunchFn find_launcher(int la, int lb, int lc, int ld) {
 #define X(a, b, c, d, tag) \
@@ -140,20 +163,16 @@ struct Batch {
   std::vector<int> shA, shB;
   std::vector<double> Q;
   double* d_prim = nullptr;
-  double* d_prim_far = nullptr;  // RCHEM_FAR_COMPRESS: compressed far-field primitives
-  int K2far = 0;
-  int same_centre = 0;           // RCHEM_FAR_COMPRESS: batch key (every pair same-centre or none)
   double* d_geom = nullptr;
   int* d_idx = nullptr;
   double* d_Dp = nullptr;  // [ncart(la)*ncart(lb)][stride] packed D blocks
   double* d_Jp = nullptr;  // [ncart(la)*ncart(lb)][stride] packed J blocks
   int ncomp() const { return ncart(la) * ncart(lb); }
+  int nv() const { return nvariants(la) * nvariants(lb); }                      // weight variants
+  int nfields() const { return kPrimFieldsBase + nv(); }                        // SoA arrays per primitive pair
+  size_t prim_bytes() const { return (size_t)nfields() * sizeof(double); }      // sizeof(PrimPairV<nv>)
   BatchView view() const {
-#if RCHEM_FAR_COMPRESS
-    return BatchView{d_prim, d_geom, d_idx, d_Dp, d_Jp, npairs, stride, K2, d_prim_far, K2far};
-#else
     return BatchView{d_prim, d_geom, d_idx, d_Dp, d_Jp, npairs, stride, K2};
-#endif
   }
 };
 
@@ -479,6 +498,10 @@ struct rchem_basis {
   cudaStream_t last_stream = nullptr;  // stream of the previous build (order_after_previous_build)
   bool last_stream_valid = false;
   int symmetric_only = 0;           // RCHEM_OPT_SYMMETRIC_D_ONLY
+  int fuse_sp = [] {                // RCHEM_OPT_FUSE_SP; the environment sets the default (tuning)
+    const char* e = std::getenv("RCHEM_FUSE_SP");
+    return e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }();
   // single-process multi-GPU (RCHEM_OPT_NGPUS): this handle drives devices device ..
   // device + ngpus - 1; peers[i-1] is a full clone of the handle living on device + i
   int ngpus = 1;
@@ -504,13 +527,8 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   const int np = bt.npairs;
   bt.stride = (np + 31) / 32 * 32;
   const size_t st = bt.stride;
-  std::vector<double> prim(kPrimFields * (size_t)bt.K2 * st, 0.0), geom(kGeomFields * st, 0.0);
-#if RCHEM_FAR_COMPRESS
-  // far-field table: same-centre batches hold min(K2, L+1) moment-matched pseudo-primitives
-  bt.K2far = bt.same_centre ? std::min(bt.K2, bt.la + bt.lb + 1) : bt.K2;
-  std::vector<double> prim_far(kPrimFields * (size_t)bt.K2far * st, 0.0);
-  std::vector<PrimPair> cps;
-#endif
+  const int nf = bt.nfields();
+  std::vector<double> prim(nf * (size_t)bt.K2 * st, 0.0), geom(kGeomFields * st, 0.0);
   std::vector<int> idx(3 * st, 0);
   std::vector<PrimPair> pps;
   std::vector<int> shA(np), shB(np);
@@ -525,21 +543,10 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
     build_significant_prim_pairs(A, B, h->prim_eps, &pps);  // pps.size() == bt.K2 by construction
     for (int k = 0; k < bt.K2; ++k) {
       const PrimPair& pp = pps[k];
-      const double f[kPrimFields] = {pp.zeta, pp.rzeta, pp.Px, pp.Py, pp.Pz, pp.pref, pp.pfar};
-      for (int c = 0; c < kPrimFields; ++c) prim[((size_t)c * bt.K2 + k) * st + s] = f[c];
+      const double f[kPrimFieldsBase + kMaxPairVariants] = {pp.zeta, pp.rzeta, pp.Px, pp.Py, pp.Pz, pp.fsc,
+                                                            pp.pfar, pp.w[0], pp.w[1], pp.w[2], pp.w[3]};
+      for (int c = 0; c < nf; ++c) prim[((size_t)c * bt.K2 + k) * st + s] = f[c];
     }
-#if RCHEM_FAR_COMPRESS
-    if (!(bt.same_centre && compress_far_prim_pairs(pps, bt.la + bt.lb, &cps) &&
-          (int)cps.size() == bt.K2far))
-      cps = pps;  // (two-centre pair, or nothing to gain)
-    if ((int)cps.size() != bt.K2far)
-      return fail(RCHEM_ERR_CUDA, "internal: far-field primitive table layout");
-    for (int k = 0; k < bt.K2far; ++k) {
-      const PrimPair& pp = cps[k];
-      const double f[kPrimFields] = {pp.zeta, pp.rzeta, pp.Px, pp.Py, pp.Pz, pp.pref, pp.pfar};
-      for (int c = 0; c < kPrimFields; ++c) prim_far[((size_t)c * bt.K2far + k) * st + s] = f[c];
-    }
-#endif
     const PairBound pb = bound_prim_pairs(pps);
     for (int d = 0; d < 3; ++d) {
       geom[d * st + s] = A.ctr[d];
@@ -555,10 +562,7 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   }
   // padding slots replicate pair 0 so stray reads stay finite
   for (int s = np; s < (int)st; ++s) {
-    for (size_t c = 0; c < kPrimFields * (size_t)bt.K2; ++c) prim[c * st + s] = prim[c * st];
-#if RCHEM_FAR_COMPRESS
-    for (size_t c = 0; c < kPrimFields * (size_t)bt.K2far; ++c) prim_far[c * st + s] = prim_far[c * st];
-#endif
+    for (size_t c = 0; c < nf * (size_t)bt.K2; ++c) prim[c * st + s] = prim[c * st];
     for (int c = 0; c < kGeomFields; ++c) geom[c * st + s] = geom[c * st];
     for (int c = 0; c < 3; ++c) idx[c * st + s] = idx[c * st];
   }
@@ -567,9 +571,6 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   if (!bt.Q.empty()) bt.Q.swap(Q);
   if (!bt.d_prim) {
     CUDA_OK(cudaMalloc(&bt.d_prim, prim.size() * sizeof(double)));
-#if RCHEM_FAR_COMPRESS
-    CUDA_OK(cudaMalloc(&bt.d_prim_far, prim_far.size() * sizeof(double)));
-#endif
     CUDA_OK(cudaMalloc(&bt.d_geom, geom.size() * sizeof(double)));
     CUDA_OK(cudaMalloc(&bt.d_idx, idx.size() * sizeof(int)));
     CUDA_OK(cudaMalloc(&bt.d_Dp, (size_t)bt.ncomp() * st * sizeof(double)));
@@ -578,10 +579,6 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   }
   CUDA_OK(cudaMemcpyAsync(bt.d_prim, prim.data(), prim.size() * sizeof(double),
                           cudaMemcpyHostToDevice, h->stream));
-#if RCHEM_FAR_COMPRESS
-  CUDA_OK(cudaMemcpyAsync(bt.d_prim_far, prim_far.data(), prim_far.size() * sizeof(double),
-                          cudaMemcpyHostToDevice, h->stream));
-#endif
   CUDA_OK(cudaMemcpyAsync(bt.d_geom, geom.data(), geom.size() * sizeof(double),
                           cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaMemcpyAsync(bt.d_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice,
@@ -598,8 +595,9 @@ void fill_common(const rchem_basis* h, EriTask* t) {
   t->boys.delta.rows = h->d_delta_rows;
   t->nranks = 1;
   t->far_sched = h->far_sched;
-  for (int l = 0; l < 3; ++l)
-    for (int k = 0; k < 6; ++k) t->compscale[l][k] = (l <= h->shells.lmax) ? h->shells.compscale[l][k] : 1.0;
+  for (int l = 0; l < kNumTypes; ++l)
+    for (int k = 0; k < 6; ++k)
+      t->compscale[l][k] = (l < 3 && l <= h->shells.lmax) ? h->shells.compscale[l][k] : 1.0;
 }
 
 void free_tasks(rchem_basis* h);
@@ -612,7 +610,7 @@ void release_device_state(rchem_basis* h) {
   if (h->device >= 0 && h->device < ndev) cudaSetDevice(h->device);
   free_tasks(h);
   for (Batch& bt : h->batches) {
-    cudaFree(bt.d_prim); cudaFree(bt.d_prim_far); cudaFree(bt.d_geom); cudaFree(bt.d_idx);
+    cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_idx);
     cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
   }
   h->batches.clear();
@@ -691,14 +689,8 @@ int ensure_ready(rchem_basis* h) {
       // K2 = number of SIGNIFICANT primitive pairs (pair_build.h kPrimPairEps)
       const int K2 = build_significant_prim_pairs(sh[a], sh[b], h->prim_eps, &scratch_pps);
       const int cls = sh[a].l * (sh[a].l + 1) / 2 + sh[b].l;
-#if RCHEM_FAR_COMPRESS
-      const int same = (sh[a].ctr[0] == sh[b].ctr[0] && sh[a].ctr[1] == sh[b].ctr[1] &&
-                        sh[a].ctr[2] == sh[b].ctr[2]) ? 1 : 0;
-#else
-      const int same = 0;
-#endif
-      Batch& bt = by_key[std::make_tuple(cls, -K2, same)];
-      bt.la = sh[a].l; bt.lb = sh[b].l; bt.K2 = K2; bt.same_centre = same;
+      Batch& bt = by_key[std::make_tuple(cls, -K2, 0)];
+      bt.la = sh[a].l; bt.lb = sh[b].l; bt.K2 = K2;
       bt.shA.push_back(a); bt.shB.push_back(b);
     }
   h->batches.clear();
@@ -719,7 +711,7 @@ int ensure_ready(rchem_basis* h) {
     EriTask t;
     fill_common(h, &t);
     t.bra = t.ket = bt.view();
-    t.boys.exact = h->d_boys + (size_t)(2 * (bt.la + bt.lb)) * kBoysTableLen;
+    t.boys.exact = h->d_boys + (size_t)(2 * (type_lmax(bt.la) + type_lmax(bt.lb))) * kBoysTableLen;
     t.nwarps = (bt.npairs + 31) / 32;
     t.same = 1;
     t.Qout = dQ;
@@ -840,7 +832,7 @@ int ensure_tasks(rchem_basis* h) {
       EriBlockInfo info{0, 0};
       find_block_launcher(B.la, B.lb, K.la, K.lb, &info);
       tt.smem_bytes = (size_t)2 * (ncart(B.la) + ncart(B.lb)) * h->N * sizeof(double) +
-                      (size_t)(B.K2 + (RCHEM_FAR_COMPRESS ? B.K2far : 0)) * sizeof(PrimPair) +
+                      (size_t)B.K2 * B.prim_bytes() +
                       (size_t)info.kets_per_block * sizeof(int) + 64;
       const bool rows_fit = tt.smem_bytes <= kMaxBlockSmem && info.threads > 0;
       // a bra pair is "heavy" when its ket prefix fills the block kernel's threads at least
@@ -872,7 +864,7 @@ int ensure_tasks(rchem_basis* h) {
         int cap = 0;
         for (int p = 0; p < B.npairs; ++p)
           if (nq_light[p] > 0) { lp.push_back(p); cap = std::max(cap, nq_light[p]); }
-        const size_t per_warp = (((size_t)(B.K2 + (RCHEM_FAR_COMPRESS ? B.K2far : 0)) * sizeof(PrimPair) +
+        const size_t per_warp = (((size_t)B.K2 * B.prim_bytes() +
                                   (size_t)cap * sizeof(int)) + 7) & ~(size_t)7;
         if (h->light_kernel && info.threads > 0 && !lp.empty() && per_warp * kWarpsPerBlock <= 40 * 1024) {
           tt.nlight = (int)lp.size();
@@ -927,7 +919,7 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
     EriTask t = proto;
     t.bra = B.view();
     t.ket = K.view();
-    t.boys.exact = h->d_boys + (size_t)(B.la + B.lb + K.la + K.lb) * kBoysTableLen;
+    t.boys.exact = h->d_boys + (size_t)(type_lmax(B.la) + type_lmax(B.lb) + type_lmax(K.la) + type_lmax(K.lb)) * kBoysTableLen;
     t.nq = tt.d_nq;
     t.same = tt.bra == tt.ket;
     t.rank = rank;
@@ -1029,19 +1021,30 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
   }
   for (TaskTable& tt : h->tasks) {
     const Batch &B = h->batches[tt.bra], &K = h->batches[tt.ket];
-    st.shell_quartets_all += tt.nquartets_all;
+    {
+      double P_, H_;
+      int ns_ = 1;
+      flop_model_types(B.la, B.lb, K.la, K.lb, &P_, &H_, &ns_);
+      st.shell_quartets_all += tt.nquartets_all * ns_;
+    }
     if (tt.nwarps == 0) continue;
     quartets_of_rank(tt, rank, nranks);
     EriTask t = make_task(tt);
     EriLaunchFn fn = find_launcher(B.la, B.lb, K.la, K.lb);
     if (!fn) return fail(RCHEM_ERR_UNSUPPORTED_AM, "no kernel for this class");
-    const FlopModel* fm = flop_model(B.la, B.lb, K.la, K.lb);
+    double fmP = 0.0, fmH = 0.0;
+    int nseg = 1;
+    const bool fm = flop_model_types(B.la, B.lb, K.la, K.lb, &fmP, &fmH, &nseg);
     const double k4 = (double)B.K2 * K.K2;
+    // counts are in SEGMENTED (s/p/d) shell quartets: a quartet of fused sp shells evaluates
+    // nseg of them (every s|p-part combination) on one set of primitive quartets
     auto account = [&](long long q) {
-      st.shell_quartets += q;
-      st.prim_quartets += (long long)(q * k4);
+      st.shell_quartets += q * nseg;
+      st.fused_quartets += q;
+      st.prim_quartets += (long long)(q * k4) * nseg;
+      st.prim_quartets_evaluated += (long long)(q * k4);
       st.integrals += q * (long long)(ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb));
-      if (fm) st.model_flops += q * (k4 * fm->P + fm->H);
+      if (fm) st.model_flops += q * (k4 * fmP + fmH);
     };
     // --- warp kernels (everything in tensor mode; the light bra pairs in J/K mode) ---
     const long long nwarps = split ? tt.nwarps_light : tt.nwarps;
@@ -1107,7 +1110,7 @@ int make_basis_handle(Basis&& basis, rchem_basis** out) {
   rchem_basis* h = new rchem_basis();
   h->basis = std::move(basis);
   std::string err;
-  if (!group_shells(h->basis, &h->shells, &err)) {
+  if (!group_shells(h->basis, &h->shells, &err, h->fuse_sp != 0)) {
     delete h;
     return fail(RCHEM_ERR_UNSUPPORTED_LAYOUT, err);
   }
@@ -1214,7 +1217,7 @@ int rchem_basis_export(const rchem_basis* h, double* origins, int32_t* powers,
 int rchem_basis_shells(const rchem_basis* h, int32_t* l, int32_t* first_function) {
   if (!h) return fail(RCHEM_ERR_INVALID_ARG, "null handle");
   for (size_t i = 0; i < h->shells.shells.size(); ++i) {
-    if (l) l[i] = h->shells.shells[i].l;
+    if (l) l[i] = h->shells.shells[i].l == kTypeSP ? RCHEM_SHELL_SP : h->shells.shells[i].l;
     if (first_function) first_function[i] = h->shells.shells[i].bf0;
   }
   return (int)h->shells.shells.size();
@@ -1276,6 +1279,17 @@ int rchem_set_option(rchem_basis* h, int key, double value) {
       if (!(value >= 0.0)) return fail(RCHEM_ERR_INVALID_ARG, "heavy_passes must be >= 0");
       h->heavy_passes = value;  // (the task tables are rebuilt by the next J/K build)
       return RCHEM_OK;
+    case RCHEM_OPT_FUSE_SP: {
+      if (h->ready) return fail(RCHEM_ERR_INVALID_ARG, "fuse_sp is fixed after the first compute call");
+      if (value != 0.0 && value != 1.0) return fail(RCHEM_ERR_INVALID_ARG, "fuse_sp must be 0 or 1");
+      ShellSet regrouped;
+      std::string err;
+      if (!group_shells(h->basis, &regrouped, &err, value != 0.0))
+        return fail(RCHEM_ERR_UNSUPPORTED_LAYOUT, err);
+      h->shells = regrouped;
+      h->fuse_sp = (int)value;
+      return RCHEM_OK;
+    }
     case RCHEM_OPT_NGPUS: {
       if (!(value >= 1.0) || value != std::floor(value) || value > 16.0)
         return fail(RCHEM_ERR_INVALID_ARG, "ngpus must be an integer in 1..16");
@@ -1307,6 +1321,7 @@ double rchem_get_option(const rchem_basis* h, int key) {
     case RCHEM_OPT_LIGHT_KERNEL: return h->light_kernel;
     case RCHEM_OPT_SYMMETRIC_D_ONLY: return h->symmetric_only;
     case RCHEM_OPT_NGPUS: return h->ngpus;
+    case RCHEM_OPT_FUSE_SP: return h->fuse_sp;
   }
   return std::numeric_limits<double>::quiet_NaN();
 }
@@ -1453,6 +1468,14 @@ int sync_peer_options(rchem_basis* h) {
     cudaGetDeviceCount(&ndev);
     peer->device = (h->device + 1 + (int)h->peers.size()) % std::max(1, ndev);
     peer->prim_eps = h->prim_eps;
+    if (peer->fuse_sp != h->fuse_sp) {
+      std::string err;
+      if (!group_shells(peer->basis, &peer->shells, &err, h->fuse_sp != 0)) {
+        rchem_basis_destroy(peer);
+        return fail(RCHEM_ERR_UNSUPPORTED_LAYOUT, err);
+      }
+      peer->fuse_sp = h->fuse_sp;
+    }
     h->peers.push_back(peer);
   }
   for (rchem_basis* peer : h->peers) {
@@ -1534,7 +1557,9 @@ int jk_direct_multi(rchem_basis* h, double* J, double* K) {
   for (int i = 1; i < n; ++i) {
     const rchem_stats& s = handle(i)->stats;
     h->stats.shell_quartets += s.shell_quartets;
+    h->stats.fused_quartets += s.fused_quartets;
     h->stats.prim_quartets += s.prim_quartets;
+    h->stats.prim_quartets_evaluated += s.prim_quartets_evaluated;
     h->stats.integrals += s.integrals;
     h->stats.model_flops += s.model_flops;
     h->stats.launches += s.launches;
@@ -1580,6 +1605,8 @@ int rchem_jk_direct(rchem_basis* h, const double* D, double* J, double* K) {
     if (rc == RCHEM_OK) rc = jk_direct_device_impl(h, dA, h->d_JK, 0, 1, 1);
     if (rc == RCHEM_OK) {
       h->stats.shell_quartets += first.shell_quartets;
+      h->stats.fused_quartets += first.fused_quartets;
+      h->stats.prim_quartets_evaluated += first.prim_quartets_evaluated;
       h->stats.prim_quartets += first.prim_quartets;
       h->stats.integrals += first.integrals;
       h->stats.model_flops += first.model_flops;

@@ -39,18 +39,12 @@ constexpr int kWarpsPerBlock = kThreads / 32;
 
 enum EriMode : int { kModeJK = 0, kModeTensor = 1, kModeSchwarz = 2 };
 
-// Device view of one shell-pair batch.  prim holds kPrimFields [K2][stride] arrays in the order
-// zeta, rzeta, Px, Py, Pz, pref, pfar; geom holds kGeomFields [stride] arrays Ax,Ay,Az,
+// Device view of one shell-pair batch.  prim holds kPrimFieldsBase + NV [K2][stride] arrays in the
+// order zeta, rzeta, Px, Py, Pz, fsc, pfar, w[0..NV) (PrimPairV, eri_core.h; NV = weight variants of
+// the pair type: 1, or 2 / 4 with fused sp shells); geom holds kGeomFields [stride] arrays Ax,Ay,Az,
 // ABx,ABy,ABz, then the pair's bounding data Mx,My,Mz,rad,zmin (pair_build.h PairBound) and its
 // Schwarz bound Q; idx holds three [stride] int arrays bfA, bfB, diag.
-constexpr int kPrimFields = 7;
 constexpr int kGeomFields = 12;
-// RCHEM_FAR_COMPRESS (round-2 groundwork, default off, NOT yet verified on a GPU): the far-only
-// code reads a second primitive table in which same-centre shell pairs are replaced by their
-// L+1 moment-matched pseudo-primitives (pair_build.h compress_far_prim_pairs).
-#ifndef RCHEM_FAR_COMPRESS
-#define RCHEM_FAR_COMPRESS 0
-#endif
 struct BatchView {
   const double* prim;
   const double* geom;
@@ -60,10 +54,6 @@ struct BatchView {
   int npairs;
   int stride;
   int K2;
-#if RCHEM_FAR_COMPRESS
-  const double* prim_far;  // [kPrimFields][K2far][stride], far-field form only (zeta, pref unused)
-  int K2far;
-#endif
 };
 
 struct EriTask {
@@ -91,38 +81,25 @@ struct EriTask {
   double* I;                     // [N]^4 dense tensor                    kModeTensor
   double* Qout;                  // [bra.npairs] Schwarz bounds           kModeSchwarz
   BoysTabs boys;                 // Boys tables (exact grid of this class's L, reference tables)
-  double compscale[3][6];        // per-l component norm ratios (basis_model.h)
+  double compscale[kNumTypes][6];  // per-type component norm ratios (basis_model.h)
 };
 
-__device__ __forceinline__ PrimPair load_prim(const BatchView& b, int k, int p) {
+template <int NV>
+__device__ __forceinline__ PrimPairV<NV> load_prim(const BatchView& b, int k, int p) {
   const size_t fs = (size_t)b.K2 * b.stride;
   const double* base = b.prim + (size_t)k * b.stride + p;
-  PrimPair pp;
+  PrimPairV<NV> pp;
   pp.zeta = __ldg(base);
   pp.rzeta = __ldg(base + fs);
   pp.Px = __ldg(base + 2 * fs);
   pp.Py = __ldg(base + 3 * fs);
   pp.Pz = __ldg(base + 4 * fs);
-  pp.pref = __ldg(base + 5 * fs);
+  pp.fsc = __ldg(base + 5 * fs);
   pp.pfar = __ldg(base + 6 * fs);  // (fields a caller does not use are dead loads, removed)
+#pragma unroll
+  for (int v = 0; v < NV; ++v) pp.w[v] = __ldg(base + (kPrimFieldsBase + v) * fs);
   return pp;
 }
-
-#if RCHEM_FAR_COMPRESS
-__device__ __forceinline__ PrimPair load_prim_far(const BatchView& b, int k, int p) {
-  const size_t fs = (size_t)b.K2far * b.stride;
-  const double* base = b.prim_far + (size_t)k * b.stride + p;
-  PrimPair pp;
-  pp.zeta = 0.0;
-  pp.rzeta = __ldg(base + fs);
-  pp.Px = __ldg(base + 2 * fs);
-  pp.Py = __ldg(base + 3 * fs);
-  pp.Pz = __ldg(base + 4 * fs);
-  pp.pref = 0.0;
-  pp.pfar = __ldg(base + 6 * fs);
-  return pp;
-}
-#endif
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -154,9 +131,8 @@ __device__ __forceinline__ BraGeom load_bra_geom(const BatchView& bra, int p) {
 // FAR: the caller has proved every primitive quartet far-field (primitive_quartet_far).
 template <class C, int LA, int LB, int LC, int LD, int BOYS, bool BRA_SMEM, bool FAR = false>
 __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const BraGeom& g,
-                                                const PrimPair* __restrict__ s_bra, int q,
+                                                const PrimPairV<C::kNVb>* __restrict__ s_bra, int q,
                                                 double* __restrict__ out, int& bfC, int& bfD) {
-  // (with RCHEM_FAR_COMPRESS and FAR, s_bra points at the bra pair's COMPRESSED primitives)
   constexpr int NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
   constexpr bool kUnroll = C::kOut <= 81;
   const double* gk = t.ket.geom + q;
@@ -171,31 +147,23 @@ __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const B
 #pragma unroll(C::kTargets <= 100 ? C::kTargets : 1)
   for (int i = 0; i < C::kTargets; ++i) acc[i] = 0.0;
 
-#if RCHEM_FAR_COMPRESS
-  const int K2b = FAR ? t.bra.K2far : t.bra.K2, K2k = FAR ? t.ket.K2far : t.ket.K2;
-#else
   const int K2b = t.bra.K2, K2k = t.ket.K2;
-#endif
   for (int kk = 0; kk < K2k; ++kk) {
-#if RCHEM_FAR_COMPRESS
-    const PrimPair pk = FAR ? load_prim_far(t.ket, kk, q) : load_prim(t.ket, kk, q);
-#else
-    const PrimPair pk = load_prim(t.ket, kk, q);
-#endif
+    const PrimPairV<C::kNVk> pk = load_prim<C::kNVk>(t.ket, kk, q);
     for (int kb = 0; kb < K2b; ++kb) {
       if (FAR) {
         primitive_quartet_far<C>(s_bra[kb], pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, acc);
       } else if (BRA_SMEM) {
         primitive_quartet<C, BOYS>(s_bra[kb], pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys, acc);
       } else {
-        const PrimPair pb = load_prim(t.bra, kb, p);
+        const PrimPairV<C::kNVb> pb = load_prim<C::kNVb>(t.bra, kb, p);
         primitive_quartet<C, BOYS>(pb, pk, g.Ax, g.Ay, g.Az, Cx, Cy, Cz, t.boys, acc);
       }
     }
   }
   C::hrr(acc, g.ABx, g.ABy, g.ABz, __ldg(gk + 3 * sk), __ldg(gk + 4 * sk), __ldg(gk + 5 * sk), out);
 
-  if (LA >= 2 || LB >= 2 || LC >= 2 || LD >= 2) {  // per-component norm ratios (d and up)
+  if (LA == 2 || LB == 2 || LC == 2 || LD == 2) {  // per-component norm ratios (d shells)
 #pragma unroll(kUnroll ? C::kOut : 1)
     for (int i = 0; i < C::kOut; ++i) {
       const int d = i % ND, c = (i / ND) % NC, b = (i / (ND * NC)) % NB, a = i / (ND * NC * NB);
@@ -390,8 +358,11 @@ template <int LA, int LB, int LC, int LD> struct BlockCfg {
   static constexpr int kTargets = EriClass<LA, LB, LC, LD>::kTargets;
   static constexpr bool kSmall = kTargets <= 9;
   static constexpr bool kMedium = !kSmall && kTargets <= 18;
-  static constexpr int kThreadsBlk = kSmall ? RCHEM_BLK_T_SMALL : 256;
-  static constexpr int kMinBlocks = kSmall ? RCHEM_BLK_MINB_SMALL : (kMedium ? 2 : 1);
+  // a fused (sp sp| bra pair has 8 D rows + 8 K rows in shared memory (160 kB at N = 1248): only
+  // one block fits an SM, so medium classes of that kind run 512 threads in it
+  static constexpr bool kWideRows = ncart(LA) + ncart(LB) >= 8;
+  static constexpr int kThreadsBlk = kSmall ? RCHEM_BLK_T_SMALL : ((kMedium && kWideRows) ? 512 : 256);
+  static constexpr int kMinBlocks = kSmall ? RCHEM_BLK_MINB_SMALL : ((kMedium && !kWideRows) ? 2 : 1);
   static constexpr int kKetsPerBlock = kThreadsBlk * RCHEM_BLK_PASSES;
 };
 
@@ -512,16 +483,11 @@ eri_jk_block_kernel(const EriTask t) {
   double* Drow_b = Drow_a + NA * N;      // [NB][N]
   double* Krow_a = Drow_b + NB * N;      // [NA][N]
   double* Krow_b = Krow_a + NA * N;      // [NB][N]
-  PrimPair* s_bra = reinterpret_cast<PrimPair*>(Krow_b + NB * N);  // [K2_bra]
-  for (int k = tid; k < t.bra.K2; k += T) s_bra[k] = load_prim(t.bra, k, p);
-#if RCHEM_FAR_COMPRESS
-  PrimPair* s_bra_far = s_bra + t.bra.K2;                            // [K2far_bra]
-  for (int k = tid; k < t.bra.K2far; k += T) s_bra_far[k] = load_prim_far(t.bra, k, p);
-  PrimPair* s_bra_end = s_bra_far + t.bra.K2far;
-#else
-  PrimPair* s_bra_far = s_bra;
-  PrimPair* s_bra_end = s_bra + t.bra.K2;
-#endif
+  using BraPrim = PrimPairV<C::kNVb>;
+  BraPrim* s_bra = reinterpret_cast<BraPrim*>(Krow_b + NB * N);  // [K2_bra]
+  for (int k = tid; k < t.bra.K2; k += T) s_bra[k] = load_prim<C::kNVb>(t.bra, k, p);
+  BraPrim* s_bra_far = s_bra;
+  BraPrim* s_bra_end = s_bra + t.bra.K2;
   const BraGeom g = load_bra_geom(t.bra, p);
   for (int a = 0; a < NA; ++a)
     for (int j = tid; j < N; j += T) {
@@ -705,22 +671,14 @@ __device__ __forceinline__ void jk_light_body(const EriTask& t, long long blk, d
   const int nq = __ldg(t.nq + p);
   const int N = t.N, sb = t.bra.stride, sk = t.ket.stride;
 
-#if RCHEM_FAR_COMPRESS
-  const int k2_staged = t.bra.K2 + t.bra.K2far;
-#else
   const int k2_staged = t.bra.K2;
-#endif
-  const size_t per_warp = (size_t)k2_staged * sizeof(PrimPair) + (size_t)t.light_cap * sizeof(int);
-  PrimPair* s_bra = reinterpret_cast<PrimPair*>(reinterpret_cast<char*>(smem) +
-                                                (size_t)wib * ((per_warp + 7) & ~(size_t)7));
+  using BraPrim = PrimPairV<C::kNVb>;
+  const size_t per_warp = (size_t)k2_staged * sizeof(BraPrim) + (size_t)t.light_cap * sizeof(int);
+  BraPrim* s_bra = reinterpret_cast<BraPrim*>(reinterpret_cast<char*>(smem) +
+                                              (size_t)wib * ((per_warp + 7) & ~(size_t)7));
   int* s_list = reinterpret_cast<int*>(s_bra + k2_staged);
-  for (int k = lane; k < t.bra.K2; k += 32) s_bra[k] = load_prim(t.bra, k, p);
-#if RCHEM_FAR_COMPRESS
-  PrimPair* s_bra_far = s_bra + t.bra.K2;
-  for (int k = lane; k < t.bra.K2far; k += 32) s_bra_far[k] = load_prim_far(t.bra, k, p);
-#else
-  PrimPair* s_bra_far = s_bra;
-#endif
+  for (int k = lane; k < t.bra.K2; k += 32) s_bra[k] = load_prim<C::kNVb>(t.bra, k, p);
+  BraPrim* s_bra_far = s_bra;
   const BraGeom g = load_bra_geom(t.bra, p);
   const int bfA = __ldg(t.bra.idx + p), bfB = __ldg(t.bra.idx + sb + p);
 

@@ -21,11 +21,14 @@ namespace rchem {
 // are the typical case (exp(-alpha beta R^2 / zeta) underflows).
 constexpr double kPrimPairEps = 1e-20;
 
-// Primitive pairs of (A,B), A-primitive major: k = i*nprim(B) + j.
+// Primitive pairs of (A,B), A-primitive major: k = i*nprim(B) + j.  Every weight variant of the
+// pair (fused sp shells: s|p part of A times s|p part of B) shares zeta, P and the Gaussian-
+// product exponential; only the contraction weights differ.
 inline void build_prim_pairs(const Shell& A, const Shell& B, std::vector<PrimPair>* out) {
   out->clear();
   const double dx = A.ctr[0] - B.ctr[0], dy = A.ctr[1] - B.ctr[1], dz = A.ctr[2] - B.ctr[2];
   const double rab2 = dx * dx + dy * dy + dz * dz;  // dist2, cints.c:282-285
+  const int nva = nvariants(A.l), nvb = nvariants(B.l);
   for (size_t i = 0; i < A.exps.size(); ++i)
     for (size_t j = 0; j < B.exps.size(); ++j) {
       const double aa = A.exps[i], ab = B.exps[j];
@@ -37,22 +40,28 @@ inline void build_prim_pairs(const Shell& A, const Shell& B, std::vector<PrimPai
       pp.Pz = (aa * A.ctr[2] + ab * B.ctr[2]) / (aa + ab);
       // exp(-aa*ab*rab2/gamma) as in cints.c:113, the 1/gamma of cints.c:112, and the
       // contraction coefficient x norm of both primitives
-      pp.pref = A.cn[i] * B.cn[j] * std::exp(-aa * ab * rab2 / pp.zeta) / pp.zeta;
-      pp.pfar = 5.5683279968317078453 * pp.pref / std::sqrt(pp.zeta);  // pi^(3/2)
+      const double e = std::exp(-aa * ab * rab2 / pp.zeta);
+      pp.nv = nva * nvb;
+      for (int v = 0; v < kMaxPairVariants; ++v) pp.w[v] = 0.0;
+      for (int va = 0; va < nva; ++va)
+        for (int vb = 0; vb < nvb; ++vb)
+          pp.w[va * nvb + vb] = (va ? A.cn2[i] : A.cn[i]) * (vb ? B.cn2[j] : B.cn[j]) * e / pp.zeta;
+      pp.fsc = 5.5683279968317078453 / std::sqrt(pp.zeta);               // pi^(3/2)
+      pp.pfar = 5.5683279968317078453 * pp.w[0] / std::sqrt(pp.zeta);
       out->push_back(pp);
     }
 }
 
-// The significant primitive pairs of (A,B): those with |pref| >= eps (at least one is kept),
-// ordered by increasing zeta.  Returns the count.
+// The significant primitive pairs of (A,B): those whose largest weight is >= eps (at least one
+// is kept), ordered by increasing zeta.  Returns the count.
 inline int build_significant_prim_pairs(const Shell& A, const Shell& B, double eps,
                                         std::vector<PrimPair>* out) {
   build_prim_pairs(A, B, out);
   std::stable_sort(out->begin(), out->end(), [](const PrimPair& x, const PrimPair& y) {
-    return std::fabs(x.pref) > std::fabs(y.pref);
+    return x.wmax() > y.wmax();
   });
   size_t n = out->size();
-  while (n > 1 && !(std::fabs((*out)[n - 1].pref) >= eps)) --n;
+  while (n > 1 && !((*out)[n - 1].wmax() >= eps)) --n;
   out->resize(n);
   // most diffuse pair first: its Boys argument is (nearly) the smallest of the shell pair,
   // which is what the kernels' near/far scheduling looks at
@@ -88,73 +97,6 @@ inline PairBound bound_prim_pairs(const std::vector<PrimPair>& pps) {
   }
   pb.rad = r2 > 0.0 ? std::sqrt(r2) * (1.0 + 1e-12) + 1e-300 : 0.0;
   return pb;
-}
-
-// Moment-matched compression of a SAME-CENTRE shell pair's primitives for the far-field form
-// (groundwork for round 2; not yet used by the engine).  With rho = 1 (primitive_quartet_far)
-// a primitive enters the [e0|f0] targets only through pfar and powers 0..L of 1/zeta, L the
-// pair's total angular momentum (each power of 1/zeta comes with one unit of angular momentum
-// in the Obara-Saika relations), and all its primitives share P.  For K2 > L+1 any n = L+1
-// pseudo-primitives (w_j, u_j) with  sum_j w_j u_j^i = sum_k pfar_k zeta_k^-i  (i = 0..n-1)
-// therefore give the same contracted targets: a 36-primitive (ss| pair becomes ONE.
-// Nodes: spread over the range of 1/zeta; weights from the Vandermonde system (long double).
-// Returns false when the pair is not same-centre (the centres P differ).
-inline bool compress_far_prim_pairs(const std::vector<PrimPair>& pps, int L,
-                                    std::vector<PrimPair>* out) {
-  out->clear();
-  if (pps.empty()) return false;
-  for (const PrimPair& pp : pps) {  // (alpha A + beta A)/(alpha + beta) may be an ulp off A
-    const double tol = 1e-13 * (1.0 + std::fabs(pps[0].Px) + std::fabs(pps[0].Py) + std::fabs(pps[0].Pz));
-    if (std::fabs(pp.Px - pps[0].Px) > tol || std::fabs(pp.Py - pps[0].Py) > tol ||
-        std::fabs(pp.Pz - pps[0].Pz) > tol)
-      return false;
-  }
-  if ((int)pps.size() <= L + 1) {  // nothing to gain: keep the primitives themselves
-    *out = pps;
-    return true;
-  }
-  const int n = L + 1;
-  std::vector<long double> u(pps.size());
-  for (size_t k = 0; k < pps.size(); ++k) u[k] = 1.0L / (long double)pps[k].zeta;
-  std::vector<long double> sorted = u;
-  std::sort(sorted.begin(), sorted.end());
-  std::vector<long double> node(n), M(n, 0.0L), w(n, 0.0L);
-  for (int j = 0; j < n; ++j) {
-    // Chebyshev-like spread over [min, max] of 1/zeta (distinct for n <= number of distinct values)
-    const long double t = n == 1 ? 0.5L : 0.5L * (1.0L - cosl(3.14159265358979323846L * (j + 0.5L) / n));
-    node[j] = sorted.front() + t * (sorted.back() - sorted.front());
-  }
-  if (n == 1) node[0] = 0.5L * (sorted.front() + sorted.back());
-  for (size_t k = 0; k < pps.size(); ++k) {
-    long double p = (long double)pps[k].pfar;
-    for (int i = 0; i < n; ++i) { M[i] += p; p *= u[k]; }
-  }
-  // solve sum_j w_j node_j^i = M_i by Gaussian elimination on the Vandermonde matrix
-  std::vector<std::vector<long double>> Amat(n, std::vector<long double>(n + 1));
-  for (int i = 0; i < n; ++i) {
-    for (int j = 0; j < n; ++j) Amat[i][j] = powl(node[j], i);
-    Amat[i][n] = M[i];
-  }
-  for (int c = 0; c < n; ++c) {
-    int piv = c;
-    for (int r = c + 1; r < n; ++r) if (fabsl(Amat[r][c]) > fabsl(Amat[piv][c])) piv = r;
-    std::swap(Amat[c], Amat[piv]);
-    if (Amat[c][c] == 0.0L) return false;
-    for (int r = 0; r < n; ++r) {
-      if (r == c) continue;
-      const long double f = Amat[r][c] / Amat[c][c];
-      for (int k = c; k <= n; ++k) Amat[r][k] -= f * Amat[c][k];
-    }
-  }
-  for (int j = 0; j < n; ++j) {
-    PrimPair q = pps[0];
-    q.rzeta = (double)node[j];
-    q.zeta = (double)(1.0L / node[j]);
-    q.pfar = (double)(Amat[j][n] / Amat[j][j]);
-    q.pref = 0.0;  // (the far-field form does not use it)
-    out->push_back(q);
-  }
-  return true;
 }
 
 // exact Boys tables for boys_exact (eri_core.h): one table per total angular momentum

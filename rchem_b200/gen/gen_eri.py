@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Code generator for the per-class ERI recurrences (Head-Gordon--Pople scheme).
 
-For every angular-momentum class (la lb|lc ld) with la>=lb, lc>=ld, (la,lb)>=(lc,ld),
-la<=LMAX this script emits straight-line C++ (usable from CUDA device code and from a
+For every class (ta tb|tc td) of shell TYPES (s, p, d and the fused sp shell, see SP below)
+with ta>=tb, tc>=td, (ta,tb)>=(tc,td) this script emits straight-line C++ (usable from CUDA device code and from a
 plain host compiler) for
 
   * the Obara--Saika vertical recurrence (VRR) that turns the scaled Boys values
@@ -30,6 +30,27 @@ import sys
 
 LMAX = 2
 AX = "xyz"
+
+# Shell TYPE codes of a class: 0 = s, 1 = p, 2 = d, 3 = sp -- a FUSED s+p shell (the "L" shells
+# of STO-3G / 6-31G: one s and one p contraction on the same exponents, basis.rs:190-201 emits
+# them as 4 consecutive functions s, px, py, pz).  A fused shell has two VARIANTS (its s part
+# and its p part) with their own contraction coefficients; a quartet of fused shells shares
+# every primitive-quartet quantity (Boys values, the whole VRR) between its variants, which
+# only differ in the weight a VRR value is accumulated with.
+SP = 3
+
+
+def variants(t):
+    return [0, 1] if t == SP else [t]
+
+
+def lmax_of(t):
+    return 1 if t == SP else t
+
+
+def functions(t):
+    """functions of a shell of type t in basis order: (variant index, l, Cartesian powers)"""
+    return [(vi, l, c) for vi, l in enumerate(variants(t)) for c in cart(l)]
 
 
 def cart(l):
@@ -135,86 +156,106 @@ class VRR:
         return self.em.tmp(expr, flops)
 
 
-def gen_class(la, lb, lc, ld):
-    L = la + lb + lc + ld
-    es = [e for l in range(la, la + lb + 1) for e in cart(l)]
-    fs = [f for l in range(lc, lc + ld + 1) for f in cart(l)]
+def gen_class(ta, tb, tc, td):
+    L = lmax_of(ta) + lmax_of(tb) + lmax_of(tc) + lmax_of(td)
+    # variants of the bra / ket shell pair: index = ia * nvar(B) + ib
+    bra_vars = [(la, lb) for la in variants(ta) for lb in variants(tb)]
+    ket_vars = [(lc, ld) for lc in variants(tc) for ld in variants(td)]
+    nvb, nvk = len(bra_vars), len(ket_vars)
+    fused = nvb * nvk > 1
     tindex = {}
-    for e in es:
-        for f in fs:
-            tindex[(e, f)] = len(tindex)
+    for vb, (la, lb) in enumerate(bra_vars):
+        for vk, (lc, ld) in enumerate(ket_vars):
+            for l in range(la, la + lb + 1):
+                for e in cart(l):
+                    for lf in range(lc, lc + ld + 1):
+                        for f in cart(lf):
+                            tindex[(vb, vk, e, f)] = len(tindex)
     nt = len(tindex)
 
     # ---- VRR ---------------------------------------------------------------
     em = Emitter()
     v = VRR(em)
     acc_lines = []
-    for (e, f), idx in tindex.items():
+    for (vb, vk, e, f), idx in tindex.items():
         name = v.val(e, f, 0)
-        acc_lines.append(f"acc[{idx}] += {name};")
-    vrr_flops = em.flops + nt  # one add per target for the contraction
+        if fused:
+            acc_lines.append(f"acc[{idx}] = fma(W[{vb * nvk + vk}], {name}, acc[{idx}]);")
+        else:
+            acc_lines.append(f"acc[{idx}] += {name};")
+    vrr_flops = em.flops + nt * (2 if fused else 1)  # one add (fma) per target for the contraction
     vrr_body = em.lines + acc_lines
 
     # ---- HRR ---------------------------------------------------------------
     hm = Emitter()
     bmemo = {}
 
-    def hb(a, b, f):
-        key = (a, b, f)
+    def hb(vb, vk, a, b, f):
+        key = (vb, vk, a, b, f)
         if key in bmemo:
             return bmemo[key]
         if sum(b) == 0:
-            r = f"acc[{tindex[(a, f)]}]"
+            r = f"acc[{tindex[(vb, vk, a, f)]}]"
         else:
             i = next(k for k in range(3) if b[k] > 0)
-            hi = hb(inc(a, i), dec(b, i), f)
-            lo = hb(a, dec(b, i), f)
+            hi = hb(vb, vk, inc(a, i), dec(b, i), f)
+            lo = hb(vb, vk, a, dec(b, i), f)
             r = hm.tmp(f"fma(AB{AX[i]}, {lo}, {hi})", 2)
         bmemo[key] = r
         return r
 
     kmemo = {}
 
-    def hk(a, b, c, d):
-        key = (a, b, c, d)
+    def hk(vb, vk, a, b, c, d):
+        key = (vb, vk, a, b, c, d)
         if key in kmemo:
             return kmemo[key]
         if sum(d) == 0:
-            r = hb(a, b, c)
+            r = hb(vb, vk, a, b, c)
         else:
             i = next(k for k in range(3) if d[k] > 0)
-            hi = hk(a, b, inc(c, i), dec(d, i))
-            lo = hk(a, b, c, dec(d, i))
+            hi = hk(vb, vk, a, b, inc(c, i), dec(d, i))
+            lo = hk(vb, vk, a, b, c, dec(d, i))
             r = hm.tmp(f"fma(CD{AX[i]}, {lo}, {hi})", 2)
         kmemo[key] = r
         return r
 
     out_lines = []
-    ca, cb, cc, cd = cart(la), cart(lb), cart(lc), cart(ld)
-    nout = len(ca) * len(cb) * len(cc) * len(cd)
+    fa, fb, fc, fd = functions(ta), functions(tb), functions(tc), functions(td)
+    nout = len(fa) * len(fb) * len(fc) * len(fd)
     o = 0
-    for a in ca:
-        for b in cb:
-            for c in cc:
-                for d in cd:
-                    out_lines.append(f"out[{o}] = {hk(a, b, c, d)};")
+    for (ia, _, a) in fa:
+        for (ib, _, b) in fb:
+            for (ic, _, c) in fc:
+                for (id_, _, d) in fd:
+                    vb = ia * len(variants(tb)) + ib
+                    vk = ic * len(variants(td)) + id_
+                    out_lines.append(f"out[{o}] = {hk(vb, vk, a, b, c, d)};")
                     o += 1
     hrr_flops = hm.flops
     hrr_body = hm.lines + out_lines
 
-    tag = f"{la}{lb}{lc}{ld}"
+    tag = f"{ta}{tb}{tc}{td}"
+    names = ["s", "p", "d", "sp"]
     src = []
     src.append(f"// generated by rchem_b200/gen/gen_eri.py -- do not edit")
-    src.append(f"// class ({'spdfg'[la]}{'spdfg'[lb]}|{'spdfg'[lc]}{'spdfg'[ld]}): {nt} VRR targets, "
+    src.append(f"// class ({names[ta]} {names[tb]}|{names[tc]} {names[td]}): {nt} contraction accumulators, "
                f"{nout} integrals, emitted flops/primitive {vrr_flops}, HRR flops {hrr_flops}")
-    src.append(f"template <> struct EriClass<{la}, {lb}, {lc}, {ld}> {{")
+    src.append(f"template <> struct EriClass<{ta}, {tb}, {tc}, {td}> {{")
     src.append(f"  static constexpr int kL = {L};")
     src.append(f"  static constexpr int kTargets = {nt};")
     src.append(f"  static constexpr int kOut = {nout};")
+    src.append(f"  static constexpr int kNVb = {nvb};  // weight variants of the bra / ket shell pair")
+    src.append(f"  static constexpr int kNVk = {nvk};")
     src.append(f"  static constexpr int kVrrFlops = {vrr_flops};")
     src.append(f"  static constexpr int kHrrFlops = {hrr_flops};")
-    src.append("  RCHEM_HD static void vrr(const double* __restrict__ F, const VrrGeom& g, "
-               "double* __restrict__ acc) {")
+    if fused:
+        src.append("  // W[vb * kNVk + vk]: contraction weight of (bra variant vb, ket variant vk)")
+        src.append("  RCHEM_HD static void vrr(const double* __restrict__ F, const VrrGeom& g, "
+                   "const double* __restrict__ W, double* __restrict__ acc) {")
+    else:
+        src.append("  RCHEM_HD static void vrr(const double* __restrict__ F, const VrrGeom& g, "
+                   "double* __restrict__ acc) {")
     used = "\n".join(vrr_body)
     for nm in ["PAx", "PAy", "PAz", "WPx", "WPy", "WPz", "QCx", "QCy", "QCz", "WQx", "WQy", "WQz",
                "oo2z", "oo2e", "oo2ze", "roz", "roe"]:
@@ -233,11 +274,18 @@ def gen_class(la, lb, lc, ld):
 
 
 def classes(lmax=LMAX):
-    pairs = [(a, b) for a in range(lmax + 1) for b in range(a + 1)]
+    """Classes over the type sets {s,p,d} (segmented shells) and {s,sp} (bases made of s and
+    fused sp shells only: STO-3G, 6-31G): (ta>=tb | tc>=td), bra pair >= ket pair in the order
+    pair(ta,tb) = ta(ta+1)/2 + tb.  (Classes mixing sp and d shells would need up to 899
+    contraction accumulators per thread; a basis with d shells keeps its s and p shells
+    segmented.)"""
     out = []
-    for i, (la, lb) in enumerate(pairs):
-        for (lc, ld) in pairs[: i + 1]:
-            out.append((la, lb, lc, ld))
+    for types in ([t for t in (0, 1, 2) if t <= lmax], [0, SP] if lmax >= 1 else []):
+        pairs = sorted(((a, b) for a in types for b in types if a >= b), key=lambda p: p[0] * (p[0] + 1) // 2 + p[1])
+        for i, (ta, tb) in enumerate(pairs):
+            for (tc, td) in pairs[: i + 1]:
+                if (ta, tb, tc, td) not in out:
+                    out.append((ta, tb, tc, td))
     return out
 
 

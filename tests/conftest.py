@@ -54,8 +54,9 @@ def hostcheck():
     csrc = os.path.join(ROOT, "rchem_b200", "csrc")
     srcs = [os.path.join(ROOT, "tests", "hostcheck.cpp"), os.path.join(csrc, "basis_model.cpp")]
     deps = srcs + [os.path.join(csrc, f) for f in ("eri_core.h", "pair_build.h", "basis_model.h")]
+    deps.append(os.path.join(ROOT, "rchem_b200", "gen", "gen_eri.py"))
     gen = os.path.join(csrc, "gen", "eri_class_list.h")
-    if not os.path.exists(gen):
+    if not os.path.exists(gen) or os.path.getmtime(gen) < os.path.getmtime(deps[-1]):
         subprocess.run([sys.executable, os.path.join(ROOT, "rchem_b200", "gen", "gen_eri.py"),
                         "--outdir", os.path.join(csrc, "gen")], check=True)
     deps.append(gen)
@@ -74,6 +75,8 @@ def hostcheck():
     H.hostcheck_last_min_x.restype = C.c_double
     H.hostcheck_last_proved_far.restype = C.c_int
     H.hostcheck_last_prims_used.restype = C.c_int
+    H.hostcheck_set_fuse.argtypes = [C.c_int]
+    H.hostcheck_set_fuse.restype = None
     return H
 
 

@@ -36,16 +36,18 @@ namespace rchem {
 #include "../rchem_b200/csrc/gen/eri_class_2220.inc"
 #include "../rchem_b200/csrc/gen/eri_class_2221.inc"
 #include "../rchem_b200/csrc/gen/eri_class_2222.inc"
+#include "../rchem_b200/csrc/gen/eri_class_3000.inc"
+#include "../rchem_b200/csrc/gen/eri_class_3030.inc"
+#include "../rchem_b200/csrc/gen/eri_class_3300.inc"
+#include "../rchem_b200/csrc/gen/eri_class_3330.inc"
+#include "../rchem_b200/csrc/gen/eri_class_3333.inc"
 
 // BOYS == kBoysFarForm (test-only value): every primitive quartet through the far-field form
 // primitive_quartet_far, whatever its x; *min_x reports the smallest Boys argument met and
 // *proved_far what the block kernel's bounding-sphere test (eri_kernel.cuh) says.
 constexpr int kBoysFarForm = 4;
-// BOYS == kBoysFarCompressed (test-only value): the far-field form with the primitives of
-// same-centre shell pairs replaced by their moment-matched pseudo-primitives
-// (compress_far_prim_pairs, pair_build.h).
-constexpr int kBoysFarCompressed = 6;
 static int g_prims_used = 0;
+static int g_fuse_sp = 0;  // hostcheck_set_fuse: group sp shells as ONE fused shell (type 3)
 static double g_min_x = 0.0;
 static int g_proved_far = 0;
 template <class C, int BOYS>
@@ -55,12 +57,7 @@ void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const She
   build_prim_pairs(A, B, &bra);
   build_prim_pairs(Cc, D, &ket);
   std::vector<double> acc(C::kTargets, 0.0);
-  if (BOYS == kBoysFarCompressed) {
-    std::vector<PrimPair> cb, ck;
-    if (compress_far_prim_pairs(bra, A.l + B.l, &cb)) bra.swap(cb);
-    if (compress_far_prim_pairs(ket, Cc.l + D.l, &ck)) ket.swap(ck);
-    g_prims_used = (int)(bra.size() * ket.size());
-  }
+  g_prims_used = (int)(bra.size() * ket.size());
   if (BOYS == kBoysFarForm) {
     g_min_x = 1e300;
     for (const PrimPair& k : ket)
@@ -77,11 +74,11 @@ void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const She
   }
   for (const PrimPair& k : ket)
     for (const PrimPair& b : bra)
-      if (BOYS == kBoysFarForm || BOYS == kBoysFarCompressed)
+      if (BOYS == kBoysFarForm)
         primitive_quartet_far<C>(b, k, A.ctr[0], A.ctr[1], A.ctr[2], Cc.ctr[0], Cc.ctr[1],
                                  Cc.ctr[2], acc.data());
       else
-        primitive_quartet<C, (BOYS == kBoysFarForm || BOYS == kBoysFarCompressed) ? kBoysExact : BOYS>(
+        primitive_quartet<C, BOYS == kBoysFarForm ? kBoysExact : BOYS>(
             b, k, A.ctr[0], A.ctr[1], A.ctr[2], Cc.ctr[0], Cc.ctr[1], Cc.ctr[2], tabs, acc.data());
   C::hrr(acc.data(), A.ctr[0] - B.ctr[0], A.ctr[1] - B.ctr[1], A.ctr[2] - B.ctr[2],
          Cc.ctr[0] - D.ctr[0], Cc.ctr[1] - D.ctr[1], Cc.ctr[2] - D.ctr[2], out);
@@ -145,7 +142,7 @@ extern "C" int hostcheck_nshells(int n, const double* origins, const int32_t* po
   Basis b = from_flat(n, origins, powers, prim_offset, exps, coefs, norms);
   ShellSet ss;
   std::string err;
-  if (!group_shells(b, &ss, &err)) return -1;
+  if (!group_shells(b, &ss, &err, g_fuse_sp != 0)) return -1;
   for (size_t i = 0; i < ss.shells.size(); ++i) {
     if (l_out) l_out[i] = ss.shells[i].l;
     if (bf0_out) bf0_out[i] = ss.shells[i].bf0;
@@ -162,24 +159,19 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
   Basis b = from_flat(n, origins, powers, prim_offset, exps, coefs, norms);
   ShellSet ss;
   std::string err;
-  if (!group_shells(b, &ss, &err)) return -1;
+  if (!group_shells(b, &ss, &err, g_fuse_sp != 0)) return -1;
   const AllTabs& T = all_tabs();
   const Shell &A = ss.shells[sa], &B = ss.shells[sb], &C = ss.shells[sc], &D = ss.shells[sd];
 #define X(la, lb, lc, ld, tag)                                                              \
   if (A.l == la && B.l == lb && C.l == lc && D.l == ld) {                                   \
+    using Cl = EriClass<la, lb, lc, ld>;                                                    \
     if (boys == kBoysReference)                                                             \
-      shell_quartet<EriClass<la, lb, lc, ld>, kBoysReference>(ss, A, B, C, D,                \
-                                                              T.tabs(la + lb + lc + ld), out); \
+      shell_quartet<Cl, kBoysReference>(ss, A, B, C, D, T.tabs(Cl::kL), out);               \
     else if (boys == kBoysFarForm)                                                          \
-      shell_quartet<EriClass<la, lb, lc, ld>, kBoysFarForm>(ss, A, B, C, D,                  \
-                                                            T.tabs(la + lb + lc + ld), out); \
-    else if (boys == kBoysFarCompressed)                                                    \
-      shell_quartet<EriClass<la, lb, lc, ld>, kBoysFarCompressed>(ss, A, B, C, D,            \
-                                                                  T.tabs(la + lb + lc + ld), out); \
+      shell_quartet<Cl, kBoysFarForm>(ss, A, B, C, D, T.tabs(Cl::kL), out);                 \
     else                                                                                    \
-      shell_quartet<EriClass<la, lb, lc, ld>, kBoysExact>(ss, A, B, C, D,                    \
-                                                          T.tabs(la + lb + lc + ld), out);  \
-    return EriClass<la, lb, lc, ld>::kOut;                                                  \
+      shell_quartet<Cl, kBoysExact>(ss, A, B, C, D, T.tabs(Cl::kL), out);                   \
+    return Cl::kOut;                                                                        \
   }
   RCHEM_ERI_CLASSES(X)
 #undef X
@@ -188,6 +180,7 @@ extern "C" int hostcheck_shell_quartet(int n, const double* origins, const int32
 
 // what the last far-form call (boys = 4) saw: smallest Boys argument, bounding-sphere verdict
 extern "C" int hostcheck_last_prims_used() { return g_prims_used; }
+extern "C" void hostcheck_set_fuse(int on) { g_fuse_sp = on; }
 extern "C" double hostcheck_last_min_x() { return g_min_x; }
 extern "C" int hostcheck_last_proved_far() { return g_proved_far; }
 

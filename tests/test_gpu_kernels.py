@@ -63,17 +63,29 @@ def oracle_jk(orc, geo, ref_or_restated, nw, basis_name, boys):
 def test_each_jk_kernel_vs_oracle(rc, orc, geo, ref_or_restated, kernel, nw, basis_name):
     for boys in (rc.BOYS_REFERENCE, rc.BOYS_EXACT):
         z, x, D, Jo, Ko = oracle_jk(orc, geo, ref_or_restated, nw, basis_name, boys)
-        b = rc.Basis.new(z, x, basis_name)
-        b.set_boys(boys)
-        force_kernel(b, kernel)
-        n = b.nbf
-        for far in (True, False):
-            b.set_far_sched(far)
-            J, K = np.zeros((n, n)), np.zeros((n, n))
-            rc.JK_direct(J, K, b, D)
-            assert np.abs(J - Jo).max() < TOL, (kernel, boys, far, np.abs(J - Jo).max())
-            assert np.abs(K - Ko).max() < TOL, (kernel, boys, far, np.abs(K - Ko).max())
-        assert b.stats()["shell_quartets"] == b.stats()["shell_quartets_all"]
+        # sp shells fused (default for STO-3G / 6-31G: classes over {s, sp}) and segmented
+        # (classes over {s, p}); 6-31G* is always segmented
+        seg_quartets = None
+        for fuse in ((True, False) if "*" not in basis_name else (False,)):
+            b = rc.Basis.new(z, x, basis_name)
+            b.set_fuse_sp(fuse)
+            assert (rc.SHELL_SP in b.shells()[0]) == fuse
+            b.set_boys(boys)
+            force_kernel(b, kernel)
+            n = b.nbf
+            for far in (True, False):
+                b.set_far_sched(far)
+                J, K = np.zeros((n, n)), np.zeros((n, n))
+                rc.JK_direct(J, K, b, D)
+                assert np.abs(J - Jo).max() < TOL, (kernel, boys, far, fuse, np.abs(J - Jo).max())
+                assert np.abs(K - Ko).max() < TOL, (kernel, boys, far, fuse, np.abs(K - Ko).max())
+            st = b.stats()
+            assert st["shell_quartets"] == st["shell_quartets_all"]
+            if fuse:
+                assert st["fused_quartets"] < st["shell_quartets"]
+                assert st["prim_quartets_evaluated"] < st["prim_quartets"]
+            else:
+                assert st["fused_quartets"] == st["shell_quartets"]
 
 
 def test_block_kernel_far_field_vs_oracle(rc, orc, geo, ref_or_restated):

@@ -159,7 +159,7 @@ def test_schwarz_bounds_and_quartet_list(rc, orc, geo):
     assert np.all(l[sa] >= l[sb])
     # Q = sqrt(max |(ab|ab)|) over the shell pair's components, exact Boys
     rng = np.random.default_rng(2)
-    ncart = lambda m: (m + 1) * (m + 2) // 2
+    ncart = rc.shell_nfun
     for p in rng.choice(len(Q), size=60, replace=False):
         fa = [first[sa[p]] + i for i in range(ncart(l[sa[p]]))]
         fb = [first[sb[p]] + i for i in range(ncart(l[sb[p]]))]

@@ -33,7 +33,9 @@ def test_library_has_sm100a_code(rc):
     assert "sm_100a" in out.stdout
 
 
-@pytest.mark.parametrize("name,nbf,nshell", [("STO-3G", 7, 5), ("6-31G", 13, 9), ("6-31G*", 19, 10)])
+# (shell counts: the sp shells of STO-3G / 6-31G stay fused -- 4 and 7 shells, as in the Basis Set
+# Exchange data; 6-31G* has a d shell and keeps s and p segmented)
+@pytest.mark.parametrize("name,nbf,nshell", [("STO-3G", 7, 4), ("6-31G", 13, 7), ("6-31G*", 19, 10)])
 def test_basis_new_matches_oracle_statement(rc, orc, geo, name, nbf, nshell):
     z, x = geo.molecule(geo.WATER_CRAWFORD)
     b = rc.Basis.new(z, x, name)
@@ -46,6 +48,9 @@ def test_basis_new_matches_oracle_statement(rc, orc, geo, name, nbf, nshell):
     assert np.abs(norms / ob.norms - 1).max() < 4e-16
     l, first = b.shells()
     assert len(l) == nshell
+    assert sum(rc.shell_nfun(v) for v in l) == nbf
+    b.set_fuse_sp(False)  # RCHEM_OPT_FUSE_SP = 0: s and p parts as separate shells
+    assert len(b.shells()[0]) == {"STO-3G": 5, "6-31G": 9, "6-31G*": 10}[name]
     # function order atom -> shell -> am -> component (basis.rs:186-203): O first, then H, H
     assert np.allclose(origins[0], x[0]) and np.allclose(origins[-1], x[2])
 
@@ -217,44 +222,69 @@ def test_far_field_form_all_21_classes(hostcheck, orc, geo):
     assert n_proved > 0.5 * n_far     # the proof is not vacuous
 
 
-def test_far_field_moment_matched_compression(hostcheck, orc, geo):
-    """Groundwork for round 2 (pair_build.h compress_far_prim_pairs): in the far-field form a
-    same-centre shell pair's primitives enter only through sum_k pfar_k zeta_k^-i, i <= L, so
-    L+1 moment-matched pseudo-primitives reproduce the contracted targets of all K2 primitives
-    -- a 36 x 36 (1s1s|1s1s) contraction becomes 1 x 1.  Checked against the uncompressed
-    far-field form for every same-centre class combination of two distant 6-31G* waters."""
-    z1, x1 = geo.molecule(geo.WATER_CRAWFORD)
-    z = np.concatenate([z1, z1])
-    x = np.concatenate([x1, x1[:, [1, 2, 0]] + np.array([31.0, -7.0, 12.0])])
-    ob = orc.make_basis(z, x, "6-31G*")
+def _fused_blocks(hostcheck, ob, boys, I_ref, only_far=False):
+    """every quartet of FUSED shells (type 3 = sp: functions s, px, py, pz) in class order"""
     ls = np.zeros(ob.n, dtype=np.int32)
     bf = np.zeros(ob.n, dtype=np.int32)
     ns = hostcheck.hostcheck_nshells(*ob.args(), ls, bf)
-    half = ns // 2
-    org, _, _, _, _, _ = ob.export() if hasattr(ob, "export") else (None,) * 6
-    full, comp = np.zeros(1296), np.zeros(1296)
-    seen, saved, worst = set(), [], 0.0
-    o_shells = [s for s in range(half) if ls[s] >= 0][:6]          # the O atom's shells come first
-    o2_shells = [s + half for s in o_shells]
-    for sa in o_shells:
-        for sb in o_shells:
-            for sc in o2_shells:
-                for sd in o2_shells:
-                    if ls[sa] < ls[sb] or ls[sc] < ls[sd] or (ls[sa], ls[sb]) < (ls[sc], ls[sd]):
+    nf = lambda t: 4 if t == 3 else (t + 1) * (t + 2) // 2
+    pair = lambda a, b: ls[a] * (ls[a] + 1) // 2 + ls[b]
+    worst, classes = 0.0, set()
+    out = np.zeros(1296)
+    for sa in range(ns):
+        for sb in range(ns):
+            if ls[sa] < ls[sb]:
+                continue
+            for sc in range(ns):
+                for sd in range(ns):
+                    if ls[sc] < ls[sd] or pair(sa, sb) < pair(sc, sd):
                         continue
-                    n = hostcheck.hostcheck_shell_quartet(*ob.args(), sa, sb, sc, sd, 4, full)
-                    if hostcheck.hostcheck_last_min_x() < 48.0:
+                    n = hostcheck.hostcheck_shell_quartet(*ob.args(), sa, sb, sc, sd, boys, out)
+                    assert n == nf(ls[sa]) * nf(ls[sb]) * nf(ls[sc]) * nf(ls[sd]), (n, ls[sa], ls[sb], ls[sc], ls[sd])
+                    if only_far and hostcheck.hostcheck_last_min_x() < 48.0:
                         continue
-                    assert hostcheck.hostcheck_shell_quartet(*ob.args(), sa, sb, sc, sd, 6, comp) == n
-                    used = hostcheck.hostcheck_last_prims_used()
-                    scale = max(np.abs(full[:n]).max(), 1e-300)
-                    worst = max(worst, np.abs(comp[:n] - full[:n]).max() / scale)
-                    seen.add((ls[sa], ls[sb], ls[sc], ls[sd]))
-                    saved.append(used)
-                    L_bra, L_ket = ls[sa] + ls[sb], ls[sc] + ls[sd]
-                    assert used <= (L_bra + 1) * (L_ket + 1)
-    assert len(seen) == 21, sorted(seen)
-    assert worst < 1e-11, worst
+                    blk = I_ref[bf[sa]:bf[sa] + nf(ls[sa]), bf[sb]:bf[sb] + nf(ls[sb]),
+                                bf[sc]:bf[sc] + nf(ls[sc]), bf[sd]:bf[sd] + nf(ls[sd])]
+                    worst = max(worst, np.abs(out[:n].reshape(blk.shape) - blk).max())
+                    classes.add((ls[sa], ls[sb], ls[sc], ls[sd]))
+    return worst, classes, ls
+
+
+def test_fused_sp_classes_against_oracle(hostcheck, orc, geo, ref_or_restated):
+    """The six classes over {s, sp}: an sp shell of STO-3G / 6-31G evaluated as ONE shell whose
+    s and p parts share every primitive quartet (generated VRR with per-variant contraction
+    weights).  Every block against the oracle's tensor, both Boys flavours, and the far-field
+    form on two distant waters."""
+    hostcheck.hostcheck_set_fuse(1)
+    try:
+        z, x = geo.molecule(geo.WATER_CRAWFORD)
+        for basis_name in ("6-31G", "STO-3G"):
+            ob = orc.make_basis(z, x, basis_name)
+            with ref_or_restated():
+                I_ref = orc.build_I(ob)
+            worst, classes, ls = _fused_blocks(hostcheck, ob, 0, I_ref)
+            assert 3 in ls and 1 not in ls  # every p shell was fused with its s partner
+            assert classes == {(0, 0, 0, 0), (3, 0, 0, 0), (3, 0, 3, 0), (3, 3, 0, 0), (3, 3, 3, 0),
+                               (3, 3, 3, 3)}, sorted(classes)
+            assert worst < 1e-12, worst
+            I_x = orc.build_I(ob, orc.BOYS_EXACT)
+            worst, _, _ = _fused_blocks(hostcheck, ob, 1, I_x)
+            assert worst < 1e-13, worst
+        # far-field form (rho-free point multipoles) of the fused classes
+        z2 = np.concatenate([z, z])
+        x2 = np.concatenate([x, x[:, [2, 0, 1]] + np.array([40.0, 9.0, -6.0])])
+        ob = orc.make_basis(z2, x2, "6-31G")
+        I_x = orc.build_I(ob, orc.BOYS_EXACT)
+        worst, classes, _ = _fused_blocks(hostcheck, ob, 4, I_x, only_far=True)
+        assert len(classes) == 6 and worst < 1e-14, (worst, sorted(classes))
+        # a basis with d shells (or a lone p shell) keeps its shells segmented
+        ob = orc.make_basis(z, x, "6-31G*")
+        ls = np.zeros(ob.n, dtype=np.int32)
+        bf = np.zeros(ob.n, dtype=np.int32)
+        ns = hostcheck.hostcheck_nshells(*ob.args(), ls, bf)
+        assert 3 not in ls[:ns] and 1 in ls[:ns] and 2 in ls[:ns]
+    finally:
+        hostcheck.hostcheck_set_fuse(0)
 
 
 def test_boys_reference_restatement_bitwise_iterations(hostcheck, orc):
@@ -314,7 +344,12 @@ def test_flop_model_is_generated(rc):
     import json
 
     fl = json.load(open(os.path.join(ROOT, "rchem_b200", "csrc", "gen", "flops.json")))
-    assert len(fl) == 21
+    assert len(fl) == 26  # 21 classes over {s,p,d} + 5 more over {s, fused sp}
+    # a fused quartet shares the VRR between its s|p variants: (sp sp|sp sp) emits 1210 flops
+    # per primitive where the 16 segmented classes it covers emit 1917
+    seg = (fl["0000"]["vrr_flops"] + 4 * fl["1000"]["vrr_flops"] + 4 * fl["1010"]["vrr_flops"]
+           + 2 * fl["1100"]["vrr_flops"] + 4 * fl["1110"]["vrr_flops"] + fl["1111"]["vrr_flops"])
+    assert fl["3333"]["vrr_flops"] < 0.65 * seg and fl["3333"]["out"] == 256
     assert fl["1111"]["hrr_flops"] == 324 and fl["2222"]["hrr_flops"] == 10586
     assert fl["1010"]["vrr_flops"] == 60
 
@@ -386,7 +421,7 @@ def test_bse_json_ingestion(rc, geo):
     # the BSE file carries more digits than the embedded 8-digit table
     assert np.abs(e / ref[3] - 1).max() < 5e-7 and np.abs(c - ref[4]).max() < 5e-8
     b = bse.basis_from_bse(open(path).read(), z, x)
-    assert len(b) == 7 and list(b.shells()[0]) == [0, 0, 1, 0, 0]
+    assert len(b) == 7 and list(b.shells()[0]) == [0, rc.SHELL_SP, 0, 0]
     # a lone d shell and a general contraction: index by position, one CGTO set per row
     custom = {"elements": {"8": {"electron_shells": [
         {"function_type": "gto", "angular_momentum": [2], "exponents": ["0.8"], "coefficients": [["1.0"]]},
