@@ -35,6 +35,9 @@ WORKLOADS = {
     "h2o32_631g": (32, "6-31G", 1e-10, "configs[3]: synthetic (H2O)_32 6-31G, N=416, direct J/K"),
     "h2o32_631gs": (32, "6-31G*", 1e-10, "configs[3]: synthetic (H2O)_32 6-31G*, N=608 (s/p/d), direct J/K"),
     "h2o10_sto3g": (10, "STO-3G", 0.0, "configs[2]: synthetic (H2O)_10 STO-3G, N=70, ERI + J/K"),
+    # dense-tensor mode only: the largest clusters whose N^4 tensor is a sensible share of HBM
+    "h2o12_631gs": (12, "6-31G*", 0.0, "dense tensor: synthetic (H2O)_12 6-31G*, N=228 (s/p/d), 21.6 GB"),
+    "h2o20_631g": (20, "6-31G", 0.0, "dense tensor: synthetic (H2O)_20 6-31G, N=260, 36.6 GB"),
 }
 DEFAULT_WORKLOAD = "h2o96_631g"
 METRIC = "ERI shell-quartets/sec (Schwarz-screened direct J/K build)"
@@ -51,6 +54,9 @@ def parse():
     ap.add_argument("--boys", default="reference", choices=["reference", "exact"],
                     help="reference = libpyquante2 Fgamma (1e-12 parity); exact = converged Boys")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget")
+    ap.add_argument("--mode", default="jk", choices=["jk", "tensor"],
+                    help="jk = Schwarz-screened direct J/K build (the headline); tensor = build_I + "
+                         "JK_inmem on the dense N^4 tensor (HBM-bound; N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle parity block")
     ap.add_argument("--parity-elements", type=int, default=8)
@@ -566,10 +572,116 @@ def run_ours(args):
     return 0
 
 
+def run_tensor(args):
+    """Dense-tensor mode: a step = build_I (every canonical quartet evaluated, all 8 permutation
+    images written: N^4 doubles) followed by JK_inmem (the tensor read once).  Both are bound by
+    HBM: algorithmic bytes = 8 N^4 written, then 8 N^4 read."""
+    import torch
+
+    import rchem_b200 as rc
+    from rchem_b200 import geometry as geo
+
+    if rc.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (rchem_b200 has no CPU path)")
+    if args.gpus != 1:
+        raise SystemExit("--mode tensor is a one-GPU measurement")
+    name = args.workload if args.workload != DEFAULT_WORKLOAD else "h2o10_sto3g"
+    z, x, basis_name, tau, desc = make_workload(name)
+    dev = torch.device("cuda", 0)
+    basis = rc.Basis.new(z, x, basis_name)
+    basis.set_boys(rc.BOYS_REFERENCE if args.boys == "reference" else rc.BOYS_EXACT)
+    n = basis.nbf
+    stream = torch.cuda.current_stream()
+    basis.set_stream(stream.cuda_stream)
+    I = torch.empty((n,) * 4, dtype=torch.float64, device=dev)
+    D = torch.from_numpy(geo.synthetic_density(n)).to(dev)
+    JK = torch.empty((2, n, n), dtype=torch.float64, device=dev)
+    nbytes = 8.0 * n ** 4
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+    hbm = 6552.3
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth)"
+    except (OSError, ValueError, KeyError):
+        peak_src = "fallback 6552.3 GB/s (MEASURED_PEAKS.json absent)"
+
+    def timed(fn, reps):
+        ms = []
+        for _ in range(reps):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return float(np.mean(ms))
+
+    build = lambda: basis.build_I_device(I.data_ptr())
+    inmem = lambda: rc.jk_inmem_device(n, I.data_ptr(), D.data_ptr(), JK.data_ptr(), stream.cuda_stream)
+    for _ in range(max(args.warmup, 1)):
+        build()
+        inmem()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    build_ms = timed(build, args.steps)
+    st = basis.stats()
+    inmem_ms = timed(inmem, args.steps)
+    clocks = sampler.stop()
+    # parity of the whole step at a size the oracle can do; otherwise sampled elements
+    J_dev, K_dev = JK[0].cpu().numpy(), JK[1].cpu().numpy()
+    parity = None
+    if not args.no_parity:
+        from oracle import oracle as orc
+        from oracle import parity as par
+
+        if orc.ref_lib() is not None:
+            orc.use_reference_kernel(True)
+        orc.set_num_threads(host_cores())
+        ob = orc.make_basis(z, x, basis_name)
+        seg = rc.Basis.new(z, x, basis_name)
+        ej, ek, els = par.sampled_jk_errors(orc, ob, seg, D.cpu().numpy(), J_dev, K_dev, 0.0,
+                                            count=args.parity_elements)
+        rng = np.random.default_rng(5)
+        q = rng.integers(0, n, size=(4000, 4)).astype(np.int32)
+        vals = orc.eval_quartets(ob, q, orc.BOYS_REFERENCE if args.boys == "reference" else orc.BOYS_EXACT)
+        got = I[q[:, 0], q[:, 1], q[:, 2], q[:, 3]].cpu().numpy()
+        parity = {"max_abs_err_I": float(np.abs(got - vals).max()), "sampled_integrals": len(q),
+                  "max_abs_err_J": ej, "max_abs_err_K": ek, "elements": len(els), "tolerance": 1e-12}
+    basis.use_own_stream()
+    step_ms = build_ms + inmem_ms
+    line = {
+        "metric": METRIC.replace("Schwarz-screened direct J/K build", "dense tensor build_I + JK_inmem"),
+        "value": st["shell_quartets"] / (step_ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "mode": "tensor", "basis": basis_name, "nbf": n,
+                   "tensor_bytes": nbytes, "shell_quartets_per_step": st["shell_quartets"],
+                   "l2_flush": "256 MiB fill before every timed launch group"},
+        "build_I_ms": build_ms, "jk_inmem_ms": inmem_ms,
+        "roofline": {"bound": "hbm", "achieved": nbytes / (build_ms * 1e-3) / 1e9, "peak": hbm,
+                     "unit": "GB/s", "frac": nbytes / (build_ms * 1e-3) / 1e9 / hbm,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "build_I: eri_kernel<..,tensor> launches + tensor_fill_kernel",
+                     "algorithmic_bytes": nbytes,
+                     "note": "8 N^4 bytes written once; the quartet kernels are FP64-bound below N~100"},
+        "roofline_jk_inmem": {"bound": "hbm", "achieved": nbytes / (inmem_ms * 1e-3) / 1e9, "peak": hbm,
+                              "unit": "GB/s", "frac": nbytes / (inmem_ms * 1e-3) / 1e9 / hbm,
+                              "kernel": "jk_inmem_kernel", "algorithmic_bytes": nbytes},
+        "gpu_launches": int(st["launches"] * args.steps + args.steps),
+        "clocks": clocks, "parity": parity,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "tensor":
+        return run_tensor(args)
     return run_ours(args)
 
 

@@ -160,10 +160,18 @@ static constexpr size_t kMaxBlockSmem = 220 * 1024;
 
 struct Batch {
   int la = 0, lb = 0, K2 = 0, npairs = 0, stride = 0;
+  // A "sub" batch holds the SEGMENTED twins -- (s s|, (p s|, (p p| -- of the fused (sp sp| shell
+  // pairs: a quartet of two such pairs has 289 contraction accumulators, far beyond the register
+  // file, so those quartets are evaluated through the segmented classes instead (J/K mode).
+  // shA/shB of a sub batch index rchem_basis::seg_shells, Q is the PARENT pair's bound (so the
+  // screened set is exactly the fused list's).
+  bool sub = false;
   std::vector<int> shA, shB;
   std::vector<double> Q;
   double* d_prim = nullptr;
   double* d_geom = nullptr;
+  float4* d_bnd = nullptr;   // single-precision bounding spheres (regime classification)
+  float* d_zminf = nullptr;
   int* d_idx = nullptr;
   double* d_Dp = nullptr;  // [ncart(la)*ncart(lb)][stride] packed D blocks
   double* d_Jp = nullptr;  // [ncart(la)*ncart(lb)][stride] packed J blocks
@@ -172,12 +180,14 @@ struct Batch {
   int nfields() const { return kPrimFieldsBase + nv(); }                        // SoA arrays per primitive pair
   size_t prim_bytes() const { return (size_t)nfields() * sizeof(double); }      // sizeof(PrimPairV<nv>)
   BatchView view() const {
-    return BatchView{d_prim, d_geom, d_idx, d_Dp, d_Jp, npairs, stride, K2};
+    return BatchView{d_prim, d_geom, d_bnd, d_zminf, d_idx, d_Dp, d_Jp, npairs, stride, K2};
   }
 };
 
 struct TaskTable {
   int bra = 0, ket = 0;
+  bool sub = false;      // both batches are sub batches (J/K mode only)
+  bool jk_skip = false;  // (sp sp|sp sp): evaluated through the sub batches in J/K mode
   long long nwarps = 0, nquartets = 0, nquartets_all = 0;
   long long* d_prefix = nullptr;  // warp chunks, every bra pair (tensor mode)
   int* d_nq = nullptr;
@@ -269,9 +279,11 @@ __global__ void pack_d_kernel(const double* __restrict__ D, int N, const int* __
     Dp[(size_t)c * stride + p] = D[(size_t)(bfA + c / nb) * N + bfB + c % nb];
 }
 
-// J from the packed pair blocks.  Every unordered function pair belongs to exactly one shell
-// pair, so this is a plain (non-atomic) scatter: J[i][j] = J[j][i] = Jp[ab] (+ Jp[ba] on a
-// diagonal shell pair, whose block holds both orders) -- i.e. J = Jh + Jh^T of the digestion.
+// J from the packed pair blocks: J[i][j] = J[j][i] += Jp[ab] (+ Jp[ba] on a diagonal shell pair,
+// whose block holds both orders) -- i.e. J = Jh + Jh^T of the digestion.  Inside one batch every
+// function pair belongs to exactly one shell pair, and the batches are finalised one after the
+// other on one stream, so the (non-atomic) accumulation is race-free; J starts from zero.  (The
+// segmented twins of fused (sp sp| pairs hold a second share of the same function pairs.)
 __global__ void finalize_j_kernel(const double* __restrict__ Jp, const int* __restrict__ idx,
                                   int npairs, int stride, int nb, int ncomp, int N,
                                   double* __restrict__ J) {
@@ -282,8 +294,8 @@ __global__ void finalize_j_kernel(const double* __restrict__ Jp, const int* __re
     const int a = c / nb, b = c % nb;
     double v = Jp[(size_t)c * stride + p];
     if (diag) v += Jp[(size_t)(b * nb + a) * stride + p];
-    J[(size_t)(bfA + a) * N + bfB + b] = v;
-    if (!diag) J[(size_t)(bfB + b) * N + bfA + a] = v;
+    J[(size_t)(bfA + a) * N + bfB + b] += v;
+    if (!diag) J[(size_t)(bfB + b) * N + bfA + a] += v;
   }
 }
 
@@ -471,7 +483,10 @@ struct rchem_basis {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   bool external_stream = false;
-  std::vector<Batch> batches;
+  std::vector<Batch> batches;      // normal batches first, then the sub batches (Batch::sub)
+  std::vector<Shell> seg_shells;   // s and p parts of fused shells, for the sub batches
+  rchem_basis* tensor_twin = nullptr;  // segmented clone that builds the dense tensor (build_I)
+  const rchem_basis* stats_src = nullptr;  // handle whose events time the last build (this one if null)
   std::vector<TaskTable> tasks;
   double tasks_tau = -1.0;
   double* d_boys = nullptr;      // exact-Boys grids, one per L
@@ -530,13 +545,16 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   const int nf = bt.nfields();
   std::vector<double> prim(nf * (size_t)bt.K2 * st, 0.0), geom(kGeomFields * st, 0.0);
   std::vector<int> idx(3 * st, 0);
+  std::vector<float4> bnd(st);
+  std::vector<float> zminf(st);
   std::vector<PrimPair> pps;
   std::vector<int> shA(np), shB(np);
   std::vector<double> Q(bt.Q.empty() ? 0 : np);
   for (int s = 0; s < np; ++s) {
     const int src = order[s];
-    const Shell& A = h->shells.shells[bt.shA[src]];
-    const Shell& B = h->shells.shells[bt.shB[src]];
+    const std::vector<Shell>& pool = bt.sub ? h->seg_shells : h->shells.shells;
+    const Shell& A = pool[bt.shA[src]];
+    const Shell& B = pool[bt.shB[src]];
     shA[s] = bt.shA[src];
     shB[s] = bt.shB[src];
     if (!bt.Q.empty()) Q[s] = bt.Q[src];
@@ -555,6 +573,9 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
     }
     geom[9 * st + s] = pb.rad;
     geom[10 * st + s] = pb.zmin;
+    const PairBoundF bf = make_pair_bound_f(pb.M[0], pb.M[1], pb.M[2], pb.rad, pb.zmin);
+    bnd[s] = make_float4(bf.Mx, bf.My, bf.Mz, bf.rad);
+    zminf[s] = bf.zmin;
     geom[11 * st + s] = bt.Q.empty() ? 0.0 : Q[s];
     idx[s] = A.bf0;
     idx[st + s] = B.bf0;
@@ -564,6 +585,8 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   for (int s = np; s < (int)st; ++s) {
     for (size_t c = 0; c < nf * (size_t)bt.K2; ++c) prim[c * st + s] = prim[c * st];
     for (int c = 0; c < kGeomFields; ++c) geom[c * st + s] = geom[c * st];
+    bnd[s] = bnd[0];
+    zminf[s] = zminf[0];
     for (int c = 0; c < 3; ++c) idx[c * st + s] = idx[c * st];
   }
   bt.shA.swap(shA);
@@ -572,6 +595,8 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   if (!bt.d_prim) {
     CUDA_OK(cudaMalloc(&bt.d_prim, prim.size() * sizeof(double)));
     CUDA_OK(cudaMalloc(&bt.d_geom, geom.size() * sizeof(double)));
+    CUDA_OK(cudaMalloc(&bt.d_bnd, bnd.size() * sizeof(float4)));
+    CUDA_OK(cudaMalloc(&bt.d_zminf, zminf.size() * sizeof(float)));
     CUDA_OK(cudaMalloc(&bt.d_idx, idx.size() * sizeof(int)));
     CUDA_OK(cudaMalloc(&bt.d_Dp, (size_t)bt.ncomp() * st * sizeof(double)));
     CUDA_OK(cudaMalloc(&bt.d_Jp, (size_t)bt.ncomp() * st * sizeof(double)));
@@ -580,6 +605,10 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   CUDA_OK(cudaMemcpyAsync(bt.d_prim, prim.data(), prim.size() * sizeof(double),
                           cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaMemcpyAsync(bt.d_geom, geom.data(), geom.size() * sizeof(double),
+                          cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(bt.d_bnd, bnd.data(), bnd.size() * sizeof(float4), cudaMemcpyHostToDevice,
+                          h->stream));
+  CUDA_OK(cudaMemcpyAsync(bt.d_zminf, zminf.data(), zminf.size() * sizeof(float),
                           cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaMemcpyAsync(bt.d_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice,
                           h->stream));
@@ -610,7 +639,7 @@ void release_device_state(rchem_basis* h) {
   if (h->device >= 0 && h->device < ndev) cudaSetDevice(h->device);
   free_tasks(h);
   for (Batch& bt : h->batches) {
-    cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_idx);
+    cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_bnd); cudaFree(bt.d_zminf); cudaFree(bt.d_idx);
     cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
   }
   h->batches.clear();
@@ -731,10 +760,61 @@ int ensure_ready(rchem_basis* h) {
     if (rc) return rc;
   }
 
+  if (h->shells.fused) {
+    // segmented twins of the fused (sp sp| pairs (see Batch::sub)
+    h->seg_shells.clear();
+    std::vector<int> seg_s(sh.size(), -1), seg_p(sh.size(), -1);
+    auto part = [&](int shell, int which) {
+      std::vector<int>& memo = which ? seg_p : seg_s;
+      if (memo[shell] < 0) {
+        Shell r = sh[shell];
+        r.l = which;
+        r.bf0 = sh[shell].bf0 + which;  // functions of an sp shell: s, px, py, pz
+        if (which) r.cn = sh[shell].cn2;
+        r.cn2.clear();
+        memo[shell] = (int)h->seg_shells.size();
+        h->seg_shells.push_back(std::move(r));
+      }
+      return memo[shell];
+    };
+    std::map<std::tuple<int, int, int>, Batch> sub_key;
+    const size_t n_normal = h->batches.size();
+    for (size_t bi = 0; bi < n_normal; ++bi) {
+      const Batch& bt = h->batches[bi];
+      if (bt.la != kTypeSP || bt.lb != kTypeSP) continue;
+      for (int p = 0; p < bt.npairs; ++p) {
+        const int A = bt.shA[p], B = bt.shB[p];
+        int twins[4][2] = {{part(A, 0), part(B, 0)}, {part(A, 1), part(B, 0)},
+                           {part(B, 1), part(A, 0)}, {part(A, 1), part(B, 1)}};
+        for (int k = 0; k < 4; ++k) {
+          if (k == 2 && A == B) continue;  // (p_A s_A| appears once on a diagonal pair
+          const Shell &X = h->seg_shells[twins[k][0]], &Y = h->seg_shells[twins[k][1]];
+          const int K2 = build_significant_prim_pairs(X, Y, h->prim_eps, &scratch_pps);
+          const int cls = X.l * (X.l + 1) / 2 + Y.l;
+          Batch& sb = sub_key[std::make_tuple(cls, -K2, 0)];
+          sb.sub = true;
+          sb.la = X.l; sb.lb = Y.l; sb.K2 = K2;
+          sb.shA.push_back(twins[k][0]); sb.shB.push_back(twins[k][1]);
+          sb.Q.push_back(bt.Q[p]);
+        }
+      }
+    }
+    for (auto& kv : sub_key) {
+      Batch sb = std::move(kv.second);
+      sb.npairs = (int)sb.shA.size();
+      std::vector<int> order(sb.npairs);
+      std::iota(order.begin(), order.end(), 0);
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return sb.Q[x] > sb.Q[y]; });
+      h->batches.push_back(std::move(sb));
+      int rc = upload_batch(h, h->batches.back(), order);
+      if (rc) return rc;
+    }
+  }
+
   {  // Schwarz row sums for the K-row fixed-point bound (eri_kernel.cuh krow_add)
     std::vector<double> R(sh.size(), 0.0);
     for (const Batch& bt : h->batches)
-      for (int p = 0; p < bt.npairs; ++p) {
+      for (int p = 0; p < bt.npairs && !bt.sub; ++p) {
         const int a = bt.shA[p], b = bt.shB[p];
         R[a] += ncart(sh[b].l) * bt.Q[p];
         if (a != b) R[b] += ncart(sh[a].l) * bt.Q[p];
@@ -758,7 +838,7 @@ int ensure_ready(rchem_basis* h) {
     std::vector<unsigned char> fwd((size_t)ns * ns, 0);
     for (size_t bi = 0; bi < h->batches.size(); ++bi) {
       const Batch& bt = h->batches[bi];
-      for (int p = 0; p < bt.npairs; ++p) {
+      for (int p = 0; p < bt.npairs && !bt.sub; ++p) {
         const int a = bt.shA[p], b = bt.shB[p];
         const long long kk = ((long long)bi << 32) | (long long)p;
         key[(size_t)a * ns + b] = key[(size_t)b * ns + a] = kk;
@@ -806,8 +886,11 @@ int ensure_tasks(rchem_basis* h) {
   for (int bi = 0; bi < (int)h->batches.size(); ++bi)
     for (int ki = 0; ki <= bi; ++ki) {
       const Batch &B = h->batches[bi], &K = h->batches[ki];
+      if (B.sub != K.sub) continue;  // the segmented twins only meet each other
       TaskTable tt;
       tt.bra = bi; tt.ket = ki;
+      tt.sub = B.sub;
+      tt.jk_skip = !B.sub && B.la == kTypeSP && B.lb == kTypeSP && K.la == kTypeSP && K.lb == kTypeSP;
       tt.h_nq.resize(B.npairs);
       tt.h_prefix.resize(B.npairs + 1);
       tt.h_prefix[0] = 0;
@@ -833,7 +916,7 @@ int ensure_tasks(rchem_basis* h) {
       find_block_launcher(B.la, B.lb, K.la, K.lb, &info);
       tt.smem_bytes = (size_t)2 * (ncart(B.la) + ncart(B.lb)) * h->N * sizeof(double) +
                       (size_t)B.K2 * B.prim_bytes() +
-                      (size_t)info.kets_per_block * sizeof(int) + 64;
+                      (size_t)info.kets_per_block * sizeof(unsigned short) + 64;
       const bool rows_fit = tt.smem_bytes <= kMaxBlockSmem && info.threads > 0;
       // a bra pair is "heavy" when its ket prefix fills the block kernel's threads at least
       // kHeavyPasses times; below that the warp-per-bra-pair kernel (no D/K row staging, no
@@ -906,6 +989,7 @@ int ensure_tasks(rchem_basis* h) {
 
 // launches every task in `mode`; fills stats
 int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
+  h->stats_src = nullptr;
   rchem_stats& st = h->stats;
   st = rchem_stats{};
   st.n_tasks = (int)h->tasks.size();
@@ -939,7 +1023,7 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
     std::map<std::tuple<int, int, int, int>, std::vector<const TaskTable*>> by_class;
     size_t total = 0;
     for (const TaskTable& tt : h->tasks) {
-      if (tt.nlight <= 0) continue;
+      if (tt.nlight <= 0 || tt.jk_skip) continue;
       const Batch &B = h->batches[tt.bra], &K = h->batches[tt.ket];
       by_class[std::make_tuple(B.la, B.lb, K.la, K.lb)].push_back(&tt);
       ++total;
@@ -1021,6 +1105,8 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
   }
   for (TaskTable& tt : h->tasks) {
     const Batch &B = h->batches[tt.bra], &K = h->batches[tt.ket];
+    // J/K: (sp sp|sp sp) runs through its segmented twins; tensor / list modes never see them
+    if (split ? tt.jk_skip : tt.sub) continue;
     {
       double P_, H_;
       int ns_ = 1;
@@ -1182,6 +1268,8 @@ void rchem_basis_destroy(rchem_basis* h) {
   if (!h) return;
   for (rchem_basis* peer : h->peers) rchem_basis_destroy(peer);
   h->peers.clear();
+  if (h->tensor_twin) rchem_basis_destroy(h->tensor_twin);
+  h->tensor_twin = nullptr;
   release_device_state(h);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -1343,11 +1431,12 @@ int rchem_use_own_stream(rchem_basis* h) {
 int rchem_get_stats(const rchem_basis* h, rchem_stats* out) {
   if (!h || !out) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
   *out = h->stats;
-  out->setup_ms = h->setup_ms;
-  if (h->ready && h->ev0 && h->stats.launches > 0) {
-    if (cudaEventSynchronize(h->ev1) == cudaSuccess) {
+  out->setup_ms = h->setup_ms + (h->tensor_twin ? h->tensor_twin->setup_ms : 0.0);
+  const rchem_basis* e = h->stats_src ? h->stats_src : h;
+  if (e->ready && e->ev0 && h->stats.launches > 0) {
+    if (cudaEventSynchronize(e->ev1) == cudaSuccess) {
       float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) out->kernel_ms = ms;
+      if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) out->kernel_ms = ms;
     }
   }
   return RCHEM_OK;
@@ -1387,6 +1476,7 @@ static int jk_direct_device_impl(rchem_basis* h, const double* D_dev, double* JK
   proto.kbound = h->kbound;
   rc = run_tasks(h, kModeJK, proto, rank, nranks);
   if (rc) return rc;
+  if (!antisym) CUDA_OK(cudaMemsetAsync(JK_dev, 0, nn * sizeof(double), h->stream));
   if (!antisym)
     for (const Batch& bt : h->batches)
       finalize_j_kernel<<<(bt.npairs + 255) / 256, 256, 0, h->stream>>>(
@@ -1409,6 +1499,35 @@ int rchem_jk_direct_device(rchem_basis* h, const double* D_dev, double* JK_dev, 
 
 int rchem_build_I_device(rchem_basis* h, double* I_dev) {
   if (!h || !I_dev) return fail(RCHEM_ERR_INVALID_ARG, "null argument");
+  if (h->shells.fused) {
+    // The dense tensor is written per canonical element by the segmented classes; a handle with
+    // fused sp shells keeps a segmented clone of itself for it (same device, stream, options).
+    if (!h->tensor_twin) {
+      Basis copy = h->basis;
+      rchem_basis* twin = nullptr;
+      int rc = make_basis_handle(std::move(copy), &twin);
+      if (rc) return rc;
+      std::string err;
+      if (!group_shells(twin->basis, &twin->shells, &err, false)) {
+        rchem_basis_destroy(twin);
+        return fail(RCHEM_ERR_UNSUPPORTED_LAYOUT, err);
+      }
+      twin->fuse_sp = 0;
+      twin->device = h->device;
+      twin->prim_eps = h->prim_eps;
+      h->tensor_twin = twin;
+    }
+    rchem_basis* t = h->tensor_twin;
+    t->boys = h->boys; t->tau = h->tau;
+    int rc = ensure_ready(h);  // (gives h its stream)
+    if (rc) return rc;
+    t->stream = h->stream;
+    t->external_stream = true;
+    rc = rchem_build_I_device(t, I_dev);
+    h->stats = t->stats;
+    h->stats_src = t;  // (the timing events of this build live in the clone)
+    return rc;
+  }
   int rc = ensure_ready(h);
   if (rc) return rc;
   CUDA_OK(cudaSetDevice(h->device));
@@ -1705,6 +1824,7 @@ int64_t rchem_schwarz(rchem_basis* h, int32_t* shell_a, int32_t* shell_b, int32_
   int64_t n = 0;
   for (size_t bi = 0; bi < h->batches.size(); ++bi) {
     const Batch& bt = h->batches[bi];
+    if (bt.sub) continue;  // (segmented twins of fused pairs: an evaluation detail, same Q)
     for (int p = 0; p < bt.npairs; ++p, ++n) {
       if (shell_a) shell_a[n] = bt.shA[p];
       if (shell_b) shell_b[n] = bt.shB[p];
@@ -1723,17 +1843,18 @@ int64_t rchem_quartet_list(rchem_basis* h, int64_t* pq, int64_t capacity) {
   rc = ensure_tasks(h);
   if (rc) return rc;
   int64_t total = 0;
-  for (const TaskTable& tt : h->tasks) total += tt.nquartets;
+  for (const TaskTable& tt : h->tasks) total += tt.sub ? 0 : tt.nquartets;
   if (!pq) return total;
   if (capacity < total) return fail(RCHEM_ERR_INVALID_ARG, "quartet list buffer too small");
   std::vector<long long> pair_off(h->batches.size() + 1, 0);
-  for (size_t i = 0; i < h->batches.size(); ++i) pair_off[i + 1] = pair_off[i] + h->batches[i].npairs;
+  for (size_t i = 0; i < h->batches.size(); ++i)  // (sub batches come last: offsets of the rest unaffected)
+    pair_off[i + 1] = pair_off[i] + h->batches[i].npairs;
   long long* d_out = nullptr;
   CUDA_OK(cudaMalloc(&d_out, std::max<int64_t>(1, total) * 2 * sizeof(long long)));
   int64_t off = 0;
   for (const TaskTable& tt : h->tasks) {
     const Batch& B = h->batches[tt.bra];
-    if (tt.nquartets == 0) continue;
+    if (tt.nquartets == 0 || tt.sub) continue;
     std::vector<long long> qprefix(B.npairs + 1, 0);
     for (int p = 0; p < B.npairs; ++p) qprefix[p + 1] = qprefix[p] + tt.h_nq[p];
     long long* d_qp = nullptr;

@@ -48,6 +48,8 @@ constexpr int kGeomFields = 12;
 struct BatchView {
   const double* prim;
   const double* geom;
+  const float4* bnd;    // [stride] {Mx, My, Mz, rad} of the pair's bounding sphere, single precision
+  const float* zminf;   // [stride] most diffuse exponent sum (rounded down)
   const int* idx;
   const double* Dp;  // [ncart(la)*ncart(lb)][stride]  D block of every pair, pair-major packed
   double* Jp;        // [ncart(la)*ncart(lb)][stride]  J block of every pair (accumulated)
@@ -364,6 +366,7 @@ template <int LA, int LB, int LC, int LD> struct BlockCfg {
   static constexpr int kThreadsBlk = kSmall ? RCHEM_BLK_T_SMALL : ((kMedium && kWideRows) ? 512 : 256);
   static constexpr int kMinBlocks = kSmall ? RCHEM_BLK_MINB_SMALL : ((kMedium && !kWideRows) ? 2 : 1);
   static constexpr int kKetsPerBlock = kThreadsBlk * RCHEM_BLK_PASSES;
+  static_assert(kKetsPerBlock <= 65535, "the block kernel's ket list holds 16-bit offsets");
 };
 
 // K rows of the block kernel in shared memory.  Shared-memory fp64 (and 64-bit integer)
@@ -410,34 +413,14 @@ __device__ __forceinline__ double krow_get(const double* row, int n_row_doubles,
 // A shell quartet is scheduled as far-field when the bounding spheres of its two shell pairs
 // prove x >= kFarProvenX for every primitive quartet (boys_exact switches to the asymptotic
 // form at kBoysXMax; the far-only code never looks at x again, so the proof must hold).
-constexpr double kFarProvenX = (double)kBoysXMax;
+constexpr float kFarProvenX = (float)kBoysXMax;
 
 
-// Scheduling regime of shell quartet (bra pair | ket pair q) from the pairs' bounding data
-// (pair_build.h PairBound): 0 = PROVED far-field (every primitive quartet has x >= 48),
-// 1 = Boys grid, proved free of the Fgamma correction, 2 = may need the correction
-// (reference flavour only; otherwise everything not far is 1).
-struct BraBound { double Mx, My, Mz, rad, zmin; };
-__device__ __forceinline__ BraBound load_bra_bound(const BatchView& bra, int p) {
-  const double* gb = bra.geom + p;
-  const int sb = bra.stride;
-  return BraBound{__ldg(gb + 6 * sb), __ldg(gb + 7 * sb), __ldg(gb + 8 * sb), __ldg(gb + 9 * sb),
-                  __ldg(gb + 10 * sb)};
-}
-template <int REGIMES>
-__device__ __forceinline__ int quartet_regime(const BraBound& b, const BatchView& ket, int q,
-                                              double xcorr, int far_on) {
-  const double* gk = ket.geom + q;
-  const int sk = ket.stride;
-  const double dx = b.Mx - __ldg(gk + 6 * sk), dy = b.My - __ldg(gk + 7 * sk),
-               dz = b.Mz - __ldg(gk + 8 * sk);
-  const double rr = b.rad + __ldg(gk + 9 * sk), zk = __ldg(gk + 10 * sk);
-  const double d2c = dx * dx + dy * dy + dz * dz;
-  const double dmin = rr > 0.0 ? sqrt(d2c) - rr : 1.0;  // (rr == 0: d^2 = d2c, no square root)
-  const double d2 = rr > 0.0 ? dmin * dmin : d2c;
-  const double lhs = b.zmin * zk * d2, zs = b.zmin + zk;  // x_min >= X  <=>  lhs >= X (zb + zk)
-  if (far_on && dmin > 0.0 && lhs >= kFarProvenX * zs) return 0;
-  return (REGIMES == 3 && !(dmin > 0.0 && lhs >= xcorr * zs)) ? 2 : 1;
+// Scheduling regime of shell quartet (bra pair | ket pair q): quartet_regime_f (eri_core.h) on the
+// pairs' single-precision bounding data (BatchView::bnd: {Mx, My, Mz, rad}, BatchView::zminf).
+__device__ __forceinline__ PairBoundF load_bound(const BatchView& b, int p) {
+  const float4 v = __ldg(b.bnd + p);
+  return PairBoundF{v.x, v.y, v.z, v.w, __ldg(b.zminf + p)};
 }
 
 template <int LA, int LB, int LC, int LD, int BOYS>
@@ -526,16 +509,18 @@ eri_jk_block_kernel(const EriTask t) {
   //     primitive quartet's x from below.  These run the far-only code (primitive_quartet_far);
   //   * grid / corrected: the general code, which handles any x; the split (same lower bound
   //     of x against ref_exact_from(L)) only decides which lanes run together.
-  int* s_list = reinterpret_cast<int*>(s_bra_end);  // [q1 - q0]
+  // (16-bit offsets from q0: a block owns at most kKetsPerBlock = 4096 kets, and the list shares
+  // the SM's shared memory with up to 200 kB of D/K rows of two resident blocks)
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(s_bra_end);  // [q1 - q0]
   const int nk = q1 - q0;
   {
-    const BraBound bb = load_bra_bound(t.bra, p);
-    const double xcorr = ref_exact_from(C::kL) + 2.0;
+    const PairBoundF bb = load_bound(t.bra, p);
+    const float xcorr = (float)(ref_exact_from(C::kL) + 2.0);
     unsigned cls_bits = 0;  // 2 bits per pass: 0 far, 1 grid, 2 corrected, 3 none
     int pass = 0;
     for (int base = 0; base < nk; base += T, ++pass) {
       const int i = base + tid;
-      const int cls = i < nk ? quartet_regime<kRegimes>(bb, t.ket, q0 + i, xcorr, t.far_sched) : 3;
+      const int cls = i < nk ? quartet_regime_f<kRegimes>(bb, load_bound(t.ket, q0 + i), kFarProvenX, xcorr, t.far_sched) : 3;
       cls_bits |= (unsigned)cls << (2 * pass);
 #pragma unroll
       for (int c = 0; c < kRegimes; ++c) {
@@ -558,7 +543,7 @@ eri_jk_block_kernel(const EriTask t) {
         int at = 0;
         if (lane == 0 && m) at = atomicAdd(&s_cnt[c], __popc(m));
         at = __shfl_sync(0xffffffffu, at, 0);
-        if (cls == c) s_list[at + __popc(m & ((1u << lane) - 1u))] = q0 + i;
+        if (cls == c) s_list[at + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
       }
     }
   }
@@ -611,7 +596,7 @@ eri_jk_block_kernel(const EriTask t) {
   // unsorted, so the block stays balanced.
   int it = tid;
   for (; it < n_far; it += T) {
-    const int q = s_list[it];
+    const int q = q0 + s_list[it];
     double out[C::kOut];
     int bfC, bfD;
     const double scale =
@@ -619,7 +604,7 @@ eri_jk_block_kernel(const EriTask t) {
     digest(q, out, scale, bfC, bfD);
   }
   for (; it < nk; it += T) {
-    const int q = s_list[it];
+    const int q = q0 + s_list[it];
     double out[C::kOut];
     int bfC, bfD;
     const double scale =
@@ -685,19 +670,24 @@ __device__ __forceinline__ void jk_light_body(const EriTask& t, long long blk, d
   // regime sort (warp-local: ballots and running cursors, no atomics)
   int n_far = 0;
   {
-    const BraBound bb = load_bra_bound(t.bra, p);
-    const double xcorr = ref_exact_from(C::kL) + 2.0;
+    const PairBoundF bb = load_bound(t.bra, p);
+    const float xcorr = (float)(ref_exact_from(C::kL) + 2.0);
     int n0 = 0, n1 = 0;
-    for (int base = 0; base < nq; base += 32) {
+    unsigned long long cls_bits = 0;  // 2 bits per pass of 32 kets (a light pair has < 1024 kets)
+    int pass = 0;
+    for (int base = 0; base < nq; base += 32, ++pass) {
       const int i = base + lane;
-      const int cls = i < nq ? quartet_regime<kRegimes>(bb, t.ket, i, xcorr, t.far_sched) : 3;
+      const int cls = i < nq ? quartet_regime_f<kRegimes>(bb, load_bound(t.ket, i), kFarProvenX, xcorr, t.far_sched) : 3;
+      if (pass < 32) cls_bits |= (unsigned long long)cls << (2 * pass);
       n0 += __popc(__ballot_sync(0xffffffffu, cls == 0));
       n1 += __popc(__ballot_sync(0xffffffffu, cls == 1));
     }
     int cur[3] = {0, n0, n0 + n1};
-    for (int base = 0; base < nq; base += 32) {
+    pass = 0;
+    for (int base = 0; base < nq; base += 32, ++pass) {
       const int i = base + lane;
-      const int cls = i < nq ? quartet_regime<kRegimes>(bb, t.ket, i, xcorr, t.far_sched) : 3;
+      const int cls = pass < 32 ? (int)((cls_bits >> (2 * pass)) & 3)
+                                : (i < nq ? quartet_regime_f<kRegimes>(bb, load_bound(t.ket, i), kFarProvenX, xcorr, t.far_sched) : 3);
 #pragma unroll
       for (int c = 0; c < kRegimes; ++c) {
         const unsigned m = __ballot_sync(0xffffffffu, cls == c);

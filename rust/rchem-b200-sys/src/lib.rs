@@ -36,6 +36,8 @@ pub struct rchem_stats {
     pub launches: i32,
     pub n_tasks: i32,
     pub setup_ms: c_double,
+    pub fused_quartets: i64,
+    pub prim_quartets_evaluated: i64,
 }
 
 pub const RCHEM_OK: c_int = 0;
@@ -48,6 +50,9 @@ pub const RCHEM_OPT_HEAVY_PASSES: c_int = 6;
 pub const RCHEM_OPT_SYMMETRIC_D_ONLY: c_int = 7;
 pub const RCHEM_OPT_LIGHT_KERNEL: c_int = 8;
 pub const RCHEM_OPT_NGPUS: c_int = 9;
+pub const RCHEM_OPT_FUSE_SP: c_int = 10;
+/// `l` reported by `rchem_basis_shells` for a fused s+p shell (s, px, py, pz).
+pub const RCHEM_SHELL_SP: i32 = -1;
 
 extern "C" {
     pub fn rchem_last_error() -> *const c_char;

@@ -66,11 +66,10 @@ void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const She
         g_min_x = std::min(g_min_x, b.zeta * k.zeta / (b.zeta + k.zeta) * (dx * dx + dy * dy + dz * dz));
       }
     const PairBound pb = bound_prim_pairs(bra), pk = bound_prim_pairs(ket);
-    const double dx = pb.M[0] - pk.M[0], dy = pb.M[1] - pk.M[1], dz = pb.M[2] - pk.M[2];
-    const double rr = pb.rad + pk.rad, d2c = dx * dx + dy * dy + dz * dz;
-    const double dmin = rr > 0.0 ? std::sqrt(d2c) - rr : 1.0;
-    const double d2 = rr > 0.0 ? dmin * dmin : d2c;
-    g_proved_far = dmin > 0.0 && pb.zmin * pk.zmin * d2 >= (double)kBoysXMax * (pb.zmin + pk.zmin);
+    // the kernels' own test (eri_core.h quartet_regime_f, single precision, conservative rounding)
+    const PairBoundF fb = make_pair_bound_f(pb.M[0], pb.M[1], pb.M[2], pb.rad, pb.zmin);
+    const PairBoundF fk = make_pair_bound_f(pk.M[0], pk.M[1], pk.M[2], pk.rad, pk.zmin);
+    g_proved_far = quartet_regime_f<2>(fb, fk, (float)kBoysXMax, 0.f, 1) == 0;
   }
   for (const PrimPair& k : ket)
     for (const PrimPair& b : bra)

@@ -1,0 +1,14 @@
+#!/bin/bash
+# round-2 GPU call D: fused sp shells with (sp sp|sp sp) through segmented twins
+mkdir -p gpurun_out
+( time timeout 2400 python -m pytest tests -m gpu -q --durations=6 ) > gpurun_out/r2d_pytest_gpu.log 2>&1
+tail -12 gpurun_out/r2d_pytest_gpu.log
+for f in 1; do
+  RCHEM_FUSE_SP=$f AB_NOBASE=1 AB_COMBOS=11 timeout 600 python tools/ab_jk.py 96 6-31G 1e-10 > gpurun_out/r2d_ab_fuse$f.txt 2>&1
+  RCHEM_FUSE_SP=$f AB_NOBASE=1 AB_COMBOS=11 timeout 600 python tools/ab_jk.py 96 STO-3G 1e-10 >> gpurun_out/r2d_ab_fuse$f.txt 2>&1
+  RCHEM_FUSE_SP=$f AB_NOBASE=1 AB_COMBOS=11 timeout 600 python tools/ab_jk.py 32 6-31G 1e-10 >> gpurun_out/r2d_ab_fuse$f.txt 2>&1
+  cat gpurun_out/r2d_ab_fuse$f.txt
+done
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed_pipe_fp64.sum,smsp__inst_executed.sum,smsp__inst_executed_op_local_ld.sum,smsp__inst_executed_op_local_st.sum,smsp__inst_executed_pipe_xu.sum,smsp__inst_executed_pipe_lsu.sum,launch__registers_per_thread,launch__grid_size,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio
+timeout 1200 ncu --metrics $M --clock-control none --kernel-name-base demangled --csv --log-file gpurun_out/r2d_launches_h2o96_631g_ref.csv python tools/prof_jk.py 96 6-31G 1e-10 0 2 > gpurun_out/r2d_ncu_launches.log 2>&1
+tail -2 gpurun_out/r2d_ncu_launches.log
