@@ -383,6 +383,9 @@ template <int LA, int LB, int LC, int LD> struct BlockCfg {
 #ifndef RCHEM_K_FIXED
 #define RCHEM_K_FIXED 1
 #endif
+#ifndef RCHEM_BOYS_SMEM
+#define RCHEM_BOYS_SMEM 0
+#endif
 __device__ __forceinline__ void krow_add(double* row, int n_row_doubles, int idx, double v,
                                          double kscale) {
 #if RCHEM_K_FIXED
@@ -547,6 +550,18 @@ eri_jk_block_kernel(const EriTask t) {
       }
     }
   }
+#if RCHEM_BOYS_SMEM
+  // A/B variant (north star: "tabulated grids staged in shared memory"): this class's exact-Boys
+  // grid slice (61.5 kB) copied into the block's shared memory; the general code reads it there.
+  // Measured against the default (__ldg through L1/L2): profiles/r02_ab_boys_smem.txt.
+  double* s_boys = reinterpret_cast<double*>(
+      (reinterpret_cast<size_t>(s_list + BlockCfg<LA, LB, LC, LD>::kKetsPerBlock) + 15) & ~(size_t)15);
+  for (int i = tid; i < kBoysTableLen; i += T) s_boys[i] = __ldg(t.boys.exact + i);
+  EriTask tl = t;
+  tl.boys.exact = s_boys;
+#else
+  const EriTask& tl = t;
+#endif
   __syncthreads();
   const int n_far = s_info[0];
 
@@ -608,7 +623,7 @@ eri_jk_block_kernel(const EriTask t) {
     double out[C::kOut];
     int bfC, bfD;
     const double scale =
-        shell_quartet<C, LA, LB, LC, LD, BOYS, true, false>(t, p, g, s_bra, q, out, bfC, bfD);
+        shell_quartet<C, LA, LB, LC, LD, BOYS, true, false>(tl, p, g, s_bra, q, out, bfC, bfD);
     digest(q, out, scale, bfC, bfD);
   }
 

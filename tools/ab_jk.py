@@ -44,8 +44,15 @@ def main():
     if os.path.exists(base) and "*" not in bas and not os.environ.get("AB_NOBASE"):
         cfgs.append(("base", {"RCHEM_B200_LIB": base}))
     combos = os.environ.get("AB_COMBOS", "00,01,10,11").split(",")  # far,light digits
-    for far, light in combos:
+    for far, light in [c for c in combos if c]:
         cfgs.append((f"new far={far} light={light}", {"RCHEM_FAR": far, "RCHEM_LIGHT": light}))
+    # AB_VARIANTS="tag|library file under rchem_b200/ (or empty)|ENV=VAL,ENV=VAL;..."
+    for spec in [v for v in os.environ.get("AB_VARIANTS", "").split(";") if v]:
+        tag, lib, envs = (spec.split("|") + ["", ""])[:3]
+        env = dict(kv.split("=", 1) for kv in envs.split(",") if kv)
+        if lib:
+            env["RCHEM_B200_LIB"] = os.path.join(ROOT, "rchem_b200", lib)
+        cfgs.append((tag, env))
     for tag, env in cfgs:
         e = dict(os.environ); e.update(env)
         p = subprocess.run([sys.executable, "-c", CHILD, nw, bas, tau, tag], env=e, capture_output=True, text=True, timeout=900)
