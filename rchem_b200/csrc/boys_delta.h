@@ -33,7 +33,9 @@ constexpr int kDeltaNearUlps = 1 << 17;
 struct BoysDeltaTables {
   const double* thr;
   const float* rows;
+  const double* direct;  // boys_reference_direct: rows[m][row][kDirectRowLen] (double)
 };
+constexpr int kDirectRowLen = 8;  // degree-7 polynomial in (x - cell centre), 64 bytes
 
 RCHEM_HD int delta_cell(double x) { return x < 4.0 ? (int)(x * 64.0) : 192 + (int)(x * 16.0); }
 RCHEM_HD double delta_center(int cell) {
@@ -97,6 +99,66 @@ RCHEM_HD void boys_reference_from_exact(double xa, double ex, const BoysDeltaTab
       p *= hex * w;
     }
     F[m] -= p;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// DIRECT form (the one the kernels use, RCHEM_BOYS_DIRECT): between two iteration-count steps the
+// reference's Fgamma_m itself is smooth --
+//   series branch:   0.5 e^-x sum_{k<=n} x^k / (a (a+1) .. (a+k)),      a = m + 1/2
+//   fraction branch: 0.5 (Gamma(a) x^-a - e^-x h_n(x)),  h_n the n-th Lentz convergent
+// -- so every (order, cell, side of the step) carries a degree-7 polynomial in double precision
+// fitted to that function in long double (truncation < 1e-17 relative on cells this narrow).
+// One 8-byte threshold read (shared with the delta form: same cells, same row numbering), one
+// 64-byte row and 7 FMAs per order; no exp, no converged Boys value, no downward recursion.
+// Past ref_exact_from_order(m) + 1 the rows hold the converged F_m (the reference differs from it
+// by < 2e-15 F there).  Valid for xa < 37; the faithful loops run in the same rare cases.
+// ---------------------------------------------------------------------------------------
+template <int L, class ExactX>
+RCHEM_HD void boys_reference_direct(double xa, const BoysDeltaTables& tab, ExactX exact_x,
+                                    double* __restrict__ F) {
+  const int cell = delta_cell(xa);
+  const double dx = xa - delta_center(cell);
+  const long long xb = ref_bits(xa);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int m = 0; m <= L; ++m) {
+    const long long tb = ref_bits(ref_tab(tab.thr + m * kDeltaCells + cell));
+    const bool near = (unsigned long long)(xb - tb + kDeltaNearUlps) < 2ULL * kDeltaNearUlps ||
+                      cell == 0 || fabs(xa - (m + 1.5)) < 1e-10;
+    if (near) {
+      double x = exact_x();
+      if (fabs(x) < 0.00000001) x = 0.00000001;  // cints.c:304
+      const double rx = 1.0 / x;
+      double xpow = sqrt(rx);
+      for (int k = 0; k < m; ++k) xpow *= rx;
+      F[m] = boys_reference_order_slow(m, x, exp(-x), xpow);
+      continue;
+    }
+    const int before = (int)((tb >> 5) & 127);
+    const int side = xb >= tb ? 1 : 0;
+    const double* row = tab.direct + ((size_t)m * kDeltaMaxRows + cell + before + side) * kDirectRowLen;
+    double c[kDirectRowLen];
+#if defined(__CUDA_ARCH__)
+    const double2* r2 = reinterpret_cast<const double2*>(row);
+#pragma unroll
+    for (int j = 0; j < kDirectRowLen / 2; ++j) {
+      const double2 v = __ldg(r2 + j);
+      c[2 * j] = v.x;
+      c[2 * j + 1] = v.y;
+    }
+#else
+    for (int j = 0; j < kDirectRowLen; ++j) c[j] = row[j];
+#endif
+    double p = c[7];
+    p = fma(p, dx, c[6]);
+    p = fma(p, dx, c[5]);
+    p = fma(p, dx, c[4]);
+    p = fma(p, dx, c[3]);
+    p = fma(p, dx, c[2]);
+    p = fma(p, dx, c[1]);
+    F[m] = fma(p, dx, c[0]);
   }
 }
 

@@ -56,6 +56,57 @@ inline long double ld_fraction_delta(int m, int n, long double x) {
   return ld_boys_exact(m, x) - fref;
 }
 
+// the reference's truncated functions themselves (boys_reference_direct)
+inline long double ld_series_ref(int m, int n, long double x) {
+  const long double a = m + 0.5L;
+  long double term = 1.0L / a, sum = term;
+  for (int k = 1; k <= n; ++k) {
+    term *= x / (a + k);
+    sum += term;
+  }
+  return 0.5L * expl(-x) * sum;
+}
+inline long double ld_fraction_ref(int m, int n, long double x) {
+  const long double a = m + 0.5L;
+  long double gam = sqrtl(3.14159265358979323846264338327950288L);
+  for (int k = 0; k < m; ++k) gam *= (k + 0.5L);
+  const long double b0 = x + 1.0L - a;
+  long double A0 = 0.0L, A1 = 1.0L, B0 = 1.0L, B1 = b0;
+  for (int j = 1; j <= n; ++j) {
+    const long double aj = -(long double)j * (j - a), bj = b0 + 2.0L * j;
+    const long double A2 = bj * A1 + aj * A0, B2 = bj * B1 + aj * B0;
+    A0 = A1; A1 = A2; B0 = B1; B1 = B2;
+  }
+  return 0.5L * (gam * powl(x, -a) - expl(-x) * (A1 / B1));
+}
+
+// degree-(NC-1) interpolant at NC Chebyshev nodes of [xc-h, xc+h] as coefficients of (x - xc)^k
+template <int NC, class Fn, class Out>
+inline void cheb_fit(Fn f, long double xc, long double h, Out* out) {
+  long double V[NC][NC + 1];
+  for (int j = 0; j < NC; ++j) {
+    const long double t = cosl((2 * j + 1) * 3.14159265358979323846264338327950288L / (2.0L * NC));
+    long double p = 1.0L;
+    for (int k = 0; k < NC; ++k) { V[j][k] = p; p *= t; }
+    V[j][NC] = f(xc + h * t);
+  }
+  for (int c = 0; c < NC; ++c) {  // Gaussian elimination with partial pivoting
+    int piv = c;
+    for (int r = c + 1; r < NC; ++r) if (fabsl(V[r][c]) > fabsl(V[piv][c])) piv = r;
+    for (int k = 0; k <= NC; ++k) std::swap(V[c][k], V[piv][k]);
+    for (int r = 0; r < NC; ++r) {
+      if (r == c) continue;
+      const long double fct = V[r][c] / V[c][c];
+      for (int k = c; k <= NC; ++k) V[r][k] -= fct * V[c][k];
+    }
+  }
+  long double hk = 1.0L;
+  for (int k = 0; k < NC; ++k) {
+    out[k] = (Out)(V[k][NC] / V[k][k] / hk);
+    hk *= h;
+  }
+}
+
 // degree-5 interpolant at 6 Chebyshev nodes of [xc-h, xc+h], returned as coefficients of
 // (x - xc)^k
 template <class Fn> inline void cheb_fit6(Fn f, long double xc, long double h, float* out) {
@@ -86,9 +137,13 @@ template <class Fn> inline void cheb_fit6(Fn f, long double xc, long double h, f
 
 // thr: [kRefMaxM+1][kDeltaCells] doubles; rows: [kRefMaxM+1][kDeltaMaxRows][kDeltaRowLen] floats.
 // Returns false if a cell holds more than one step or the layout limits are exceeded.
-inline bool build_boys_delta_tables(std::vector<double>* thr, std::vector<float>* rows) {
+// direct (optional): [kRefMaxM+1][kDeltaMaxRows][kDirectRowLen] doubles, the reference's Fgamma_m
+// itself per (cell, side) -- boys_reference_direct.
+inline bool build_boys_delta_tables(std::vector<double>* thr, std::vector<float>* rows,
+                                    std::vector<double>* direct = nullptr) {
   thr->assign((size_t)(kRefMaxM + 1) * kDeltaCells, 0.0);
   rows->assign((size_t)(kRefMaxM + 1) * kDeltaMaxRows * kDeltaRowLen, 0.0f);
+  if (direct) direct->assign((size_t)(kRefMaxM + 1) * kDeltaMaxRows * kDirectRowLen, 0.0);
   bool ok = true;
   for (int m = 0; m <= kRefMaxM; ++m) {
     const double a = m + 0.5;
@@ -106,14 +161,20 @@ inline bool build_boys_delta_tables(std::vector<double>* thr, std::vector<float>
         __builtin_memcpy(&r, &b, 8);
         return r;
       };
-      if (c == 0 || lo >= cut) { *t = encode(1e300, 0); continue; }
+      const long double xc = 0.5L * ((long double)lo + hi), h = 0.5L * ((long double)hi - lo);
+      if (c == 0 || lo >= cut) {
+        *t = encode(1e300, 0);
+        if (direct && c + before < kDeltaMaxRows)  // converged F_m (cell 0 always takes the faithful loops)
+          cheb_fit<kDirectRowLen>([&](long double x) { return ld_boys_exact(m, x); }, xc, h,
+                                  direct->data() + ((size_t)m * kDeltaMaxRows + c + before) * kDirectRowLen);
+        continue;
+      }
       const bool series = lo < a + 1.0;
       const int n_lo = ref_iterations(m, lo), n_hi = ref_iterations(m, std::nextafter(hi, 0.0));
       const bool step = n_lo != n_hi;
       if (step && n_hi != n_lo + (series ? 1 : -1)) ok = false;
       if (n_lo > 30 || before > 126) ok = false;
       *t = encode(step ? ref_step(m, lo, std::nextafter(hi, 0.0), n_lo) : 1e300, n_lo);
-      const long double xc = 0.5L * ((long double)lo + hi), h = 0.5L * ((long double)hi - lo);
       for (int side = 0; side <= (step ? 1 : 0); ++side) {
         const int n = side ? n_hi : n_lo;
         const size_t r = (size_t)m * kDeltaMaxRows + c + before + side;
@@ -121,6 +182,11 @@ inline bool build_boys_delta_tables(std::vector<double>* thr, std::vector<float>
         float* out = rows->data() + r * kDeltaRowLen;
         if (series) cheb_fit6([&](long double x) { return ld_series_tail_g(m, n, x); }, xc, h, out);
         else cheb_fit6([&](long double x) { return ld_fraction_delta(m, n, x); }, xc, h, out);
+        if (direct) {
+          double* dout = direct->data() + r * kDirectRowLen;
+          if (series) cheb_fit<kDirectRowLen>([&](long double x) { return ld_series_ref(m, n, x); }, xc, h, dout);
+          else cheb_fit<kDirectRowLen>([&](long double x) { return ld_fraction_ref(m, n, x); }, xc, h, dout);
+        }
       }
       if (step) ++before;
     }

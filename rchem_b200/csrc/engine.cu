@@ -492,6 +492,7 @@ struct rchem_basis {
   double* d_boys = nullptr;      // exact-Boys grids, one per L
   double* d_delta_thr = nullptr; // boys_delta.h tables
   float* d_delta_rows = nullptr;
+  double* d_delta_direct = nullptr;
   double *d_D = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
   double* d_dmax = nullptr;  // max|D| of the current build (device scalar)
   // merged light launches (one per class): task descriptors and block prefixes
@@ -544,7 +545,7 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
   const size_t st = bt.stride;
   const int nf = bt.nfields();
   std::vector<double> prim(nf * (size_t)bt.K2 * st, 0.0), geom(kGeomFields * st, 0.0);
-  std::vector<int> idx(3 * st, 0);
+  std::vector<int> idx(4 * st, 0);
   std::vector<float4> bnd(st);
   std::vector<float> zminf(st);
   std::vector<PrimPair> pps;
@@ -580,6 +581,9 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
     idx[s] = A.bf0;
     idx[st + s] = B.bf0;
     idx[2 * st + s] = (bt.shA[src] == bt.shB[src]) ? 1 : 0;
+    // packed form for the J/K block / light kernels (only read when N < 32768)
+    idx[3 * st + s] = (int)(((unsigned)A.bf0 & 0x7fffu) | (((unsigned)B.bf0 & 0x7fffu) << 15) |
+                            ((unsigned)idx[2 * st + s] << 30));
   }
   // padding slots replicate pair 0 so stray reads stay finite
   for (int s = np; s < (int)st; ++s) {
@@ -587,7 +591,7 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
     for (int c = 0; c < kGeomFields; ++c) geom[c * st + s] = geom[c * st];
     bnd[s] = bnd[0];
     zminf[s] = zminf[0];
-    for (int c = 0; c < 3; ++c) idx[c * st + s] = idx[c * st];
+    for (int c = 0; c < 4; ++c) idx[c * st + s] = idx[c * st];
   }
   bt.shA.swap(shA);
   bt.shB.swap(shB);
@@ -622,6 +626,7 @@ void fill_common(const rchem_basis* h, EriTask* t) {
   t->boys.exact = h->d_boys;
   t->boys.delta.thr = h->d_delta_thr;
   t->boys.delta.rows = h->d_delta_rows;
+  t->boys.delta.direct = h->d_delta_direct;
   t->nranks = 1;
   t->far_sched = h->far_sched;
   for (int l = 0; l < kNumTypes; ++l)
@@ -644,7 +649,7 @@ void release_device_state(rchem_basis* h) {
   }
   h->batches.clear();
   auto drop = [](auto*& ptr) { if (ptr) cudaFree(ptr); ptr = nullptr; };
-  drop(h->d_boys); drop(h->d_delta_thr); drop(h->d_delta_rows); drop(h->d_D); drop(h->d_Kh);
+  drop(h->d_boys); drop(h->d_delta_thr); drop(h->d_delta_rows); drop(h->d_delta_direct); drop(h->d_D); drop(h->d_Kh);
   drop(h->d_JK); drop(h->d_dmax); drop(h->d_light_tasks); drop(h->d_light_prefix);
   drop(h->d_fn_shell); drop(h->d_pair_key); drop(h->d_pair_fwd); drop(h->d_asym);
   if (h->h_light_tasks) cudaFreeHost(h->h_light_tasks);
@@ -700,12 +705,15 @@ int ensure_ready(rchem_basis* h) {
   CUDA_OK(cudaMemcpy(h->d_boys, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
   std::vector<double> dthr;
   std::vector<float> drows;
-  if (!build_boys_delta_tables(&dthr, &drows))
+  std::vector<double> ddirect;
+  if (!build_boys_delta_tables(&dthr, &drows, &ddirect))
     return fail(RCHEM_ERR_CUDA, "internal: reference-Boys correction table layout exceeded");
   CUDA_OK(cudaMalloc(&h->d_delta_thr, dthr.size() * sizeof(double)));
   CUDA_OK(cudaMalloc(&h->d_delta_rows, drows.size() * sizeof(float)));
   CUDA_OK(cudaMemcpy(h->d_delta_thr, dthr.data(), dthr.size() * sizeof(double), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(h->d_delta_rows, drows.data(), drows.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&h->d_delta_direct, ddirect.size() * sizeof(double)));
+  CUDA_OK(cudaMemcpy(h->d_delta_direct, ddirect.data(), ddirect.size() * sizeof(double), cudaMemcpyHostToDevice));
 
   // shell pairs -> batches keyed by (la, lb, K2); batch order = pair class, then K2 descending
   const auto& sh = h->shells.shells;
@@ -916,11 +924,13 @@ int ensure_tasks(rchem_basis* h) {
       find_block_launcher(B.la, B.lb, K.la, K.lb, &info);
       tt.smem_bytes = (size_t)2 * (ncart(B.la) + ncart(B.lb)) * h->N * sizeof(double) +
                       (size_t)B.K2 * B.prim_bytes() +
-                      (size_t)info.kets_per_block * sizeof(unsigned short) + 64;
+                      (size_t)(info.kets_per_block + 96) * sizeof(unsigned short) + 64;
       // (A/B variant library built with -DRCHEM_BOYS_SMEM=1: room for the Boys grid slice)
       static const bool kBoysSmem = std::getenv("RCHEM_BOYS_SMEM") && atoi(std::getenv("RCHEM_BOYS_SMEM"));
       if (kBoysSmem) tt.smem_bytes += (size_t)kBoysTableLen * sizeof(double) + 16;
-      const bool rows_fit = tt.smem_bytes <= kMaxBlockSmem && info.threads > 0;
+      // (the block and light kernels read the ket pair's functions from a packed 15 + 15 bit word)
+      const bool packed_ok = h->N < 32768;
+      const bool rows_fit = tt.smem_bytes <= kMaxBlockSmem && info.threads > 0 && packed_ok;
       // a bra pair is "heavy" when its ket prefix fills the block kernel's threads at least
       // kHeavyPasses times; below that the warp-per-bra-pair kernel (no D/K row staging, no
       // block-wide barriers) is the faster home
@@ -952,7 +962,7 @@ int ensure_tasks(rchem_basis* h) {
           if (nq_light[p] > 0) { lp.push_back(p); cap = std::max(cap, nq_light[p]); }
         const size_t per_warp = (((size_t)B.K2 * B.prim_bytes() +
                                   (size_t)cap * sizeof(int)) + 7) & ~(size_t)7;
-        if (h->light_kernel && info.threads > 0 && !lp.empty() && per_warp * kWarpsPerBlock <= 40 * 1024) {
+        if (h->light_kernel && packed_ok && info.threads > 0 && !lp.empty() && per_warp * kWarpsPerBlock <= 40 * 1024) {
           tt.nlight = (int)lp.size();
           tt.h_lp = lp;
           tt.light_cap = cap;

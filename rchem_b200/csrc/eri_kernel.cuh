@@ -43,7 +43,8 @@ enum EriMode : int { kModeJK = 0, kModeTensor = 1, kModeSchwarz = 2 };
 // order zeta, rzeta, Px, Py, Pz, fsc, pfar, w[0..NV) (PrimPairV, eri_core.h; NV = weight variants of
 // the pair type: 1, or 2 / 4 with fused sp shells); geom holds kGeomFields [stride] arrays Ax,Ay,Az,
 // ABx,ABy,ABz, then the pair's bounding data Mx,My,Mz,rad,zmin (pair_build.h PairBound) and its
-// Schwarz bound Q; idx holds three [stride] int arrays bfA, bfB, diag.
+// Schwarz bound Q; idx holds four [stride] int arrays bfA, bfB, diag and the packed word
+// bfA | bfB << 15 | diag << 30 (valid for N < 32768: the J/K block and light kernels).
 constexpr int kGeomFields = 12;
 struct BatchView {
   const double* prim;
@@ -140,6 +141,9 @@ __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const B
   const double* gk = t.ket.geom + q;
   const int sk = t.ket.stride;
   const double Cx = __ldg(gk), Cy = __ldg(gk + sk), Cz = __ldg(gk + 2 * sk);
+  // J/K kernels: first functions and diagonal flag of the ket pair in ONE word, requested before
+  // the primitive loop so the digestion does not wait for it (bfC | bfD << 15 | diag << 30)
+  const unsigned cdx = BRA_SMEM ? __ldg(reinterpret_cast<const unsigned*>(t.ket.idx) + 3 * sk + q) : 0u;
 
   // Small classes keep the contraction accumulators in registers (fully unrolled init ->
   // scalar replacement).  Past ~100 targets they cannot fit; a rolled init loop indexes the
@@ -172,12 +176,20 @@ __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const B
       out[i] *= t.compscale[LA][a] * t.compscale[LB][b] * t.compscale[LC][c] * t.compscale[LD][d];
     }
   }
-  bfC = __ldg(t.ket.idx + q);
-  bfD = __ldg(t.ket.idx + sk + q);
+  int kdiag;
+  if (BRA_SMEM) {
+    bfC = (int)(cdx & 0x7fffu);
+    bfD = (int)((cdx >> 15) & 0x7fffu);
+    kdiag = (int)(cdx >> 30);
+  } else {
+    bfC = __ldg(t.ket.idx + q);
+    bfD = __ldg(t.ket.idx + sk + q);
+    kdiag = __ldg(t.ket.idx + 2 * sk + q);
+  }
   // degeneracy of the shell quartet under the 8 index permutations
   double scale = 1.0;
   if (g.diag) scale *= 0.5;
-  if (__ldg(t.ket.idx + 2 * sk + q)) scale *= 0.5;
+  if (kdiag) scale *= 0.5;
   if (t.same && p == q) scale *= 0.5;
   return scale;
 }
@@ -383,9 +395,6 @@ template <int LA, int LB, int LC, int LD> struct BlockCfg {
 #ifndef RCHEM_K_FIXED
 #define RCHEM_K_FIXED 1
 #endif
-#ifndef RCHEM_BOYS_SMEM
-#define RCHEM_BOYS_SMEM 0
-#endif
 __device__ __forceinline__ void krow_add(double* row, int n_row_doubles, int idx, double v,
                                          double kscale) {
 #if RCHEM_K_FIXED
@@ -514,8 +523,14 @@ eri_jk_block_kernel(const EriTask t) {
   //     of x against ref_exact_from(L)) only decides which lanes run together.
   // (16-bit offsets from q0: a block owns at most kKetsPerBlock = 4096 kets, and the list shares
   // the SM's shared memory with up to 200 kB of D/K rows of two resident blocks)
-  unsigned short* s_list = reinterpret_cast<unsigned short*>(s_bra_end);  // [q1 - q0]
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(s_bra_end);  // [nk + 32 kRegimes]
   const int nk = q1 - q0;
+  // The list is laid out [corrected | grid | far], each regime padded to a whole warp chunk with
+  // kEmpty entries, and the warps DRAW 32-ket chunks from a shared counter, most expensive regime
+  // first: with a static split the warps that happened to hold the general-code kets reached the
+  // final barrier long after the others (ncu: 11-19 % of all warp samples waiting there).
+  constexpr unsigned short kEmpty = 0xffffu;
+  int far_chunk0, nchunks;
   {
     const PairBoundF bb = load_bound(t.bra, p);
     const float xcorr = (float)(ref_exact_from(C::kL) + 2.0);
@@ -532,9 +547,17 @@ eri_jk_block_kernel(const EriTask t) {
       }
     }
     __syncthreads();
-    const int n0 = s_cnt[0], n1 = s_cnt[1];
+    const int n0 = s_cnt[0], n1 = s_cnt[1], n2 = s_cnt[2];  // (n2 = 0 with two regimes)
+    const int p0 = (n0 + 31) & ~31, p1 = (n1 + 31) & ~31, p2 = (n2 + 31) & ~31;
+    far_chunk0 = (p2 + p1) >> 5;
+    nchunks = (p2 + p1 + p0) >> 5;
     __syncthreads();
-    if (tid == 0) { s_info[0] = n0; s_cnt[0] = 0; s_cnt[1] = n0; s_cnt[2] = n0 + n1; }  // cursors
+    if (tid == 0) { s_cnt[2] = 0; s_cnt[1] = p2; s_cnt[0] = p2 + p1; s_info[0] = 0; }  // cursors, chunk counter
+    if (tid < 32) {
+      if (n2 + tid < p2) s_list[n2 + tid] = kEmpty;
+      if (n1 + tid < p1) s_list[p2 + n1 + tid] = kEmpty;
+      if (n0 + tid < p0) s_list[p2 + p1 + n0 + tid] = kEmpty;
+    }
     __syncthreads();
     pass = 0;
     for (int base = 0; base < nk; base += T, ++pass) {
@@ -555,7 +578,7 @@ eri_jk_block_kernel(const EriTask t) {
   // grid slice (61.5 kB) copied into the block's shared memory; the general code reads it there.
   // Measured against the default (__ldg through L1/L2): profiles/r02_ab_boys_smem.txt.
   double* s_boys = reinterpret_cast<double*>(
-      (reinterpret_cast<size_t>(s_list + BlockCfg<LA, LB, LC, LD>::kKetsPerBlock) + 15) & ~(size_t)15);
+      (reinterpret_cast<size_t>(s_list + BlockCfg<LA, LB, LC, LD>::kKetsPerBlock + 96) + 15) & ~(size_t)15);
   for (int i = tid; i < kBoysTableLen; i += T) s_boys[i] = __ldg(t.boys.exact + i);
   EriTask tl = t;
   tl.boys.exact = s_boys;
@@ -563,7 +586,6 @@ eri_jk_block_kernel(const EriTask t) {
   const EriTask& tl = t;
 #endif
   __syncthreads();
-  const int n_far = s_info[0];
 
   // digestion of one evaluated shell quartet (bra pair p | ket pair q) into J and K
   auto digest = [&](int q, const double* __restrict__ out, double scale, int bfC, int bfD) {
@@ -606,25 +628,30 @@ eri_jk_block_kernel(const EriTask t) {
     for (int i = 0; i < NB * ND; ++i) krow_add(Krow_b, NB * N, (i / ND) * N + bfD + i % ND, kbd[i], kscale);
   };
 
-  // Every thread walks the sorted list with stride T: far items first (all warps together in
-  // the early passes), then the general ones -- the per-thread item count is what it would be
-  // unsorted, so the block stays balanced.
-  int it = tid;
-  for (; it < n_far; it += T) {
-    const int q = q0 + s_list[it];
+  // Every warp draws chunks until the list is exhausted: general-code chunks (corrected, then
+  // grid) first, the cheap uniform far-field chunks last, so the warps finish together.
+  for (;;) {
+    int c = 0;
+    if (lane == 0) c = atomicAdd(&s_info[0], 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= nchunks) break;
+    const unsigned short e = s_list[c * 32 + lane];
+    const int q = q0 + e;
     double out[C::kOut];
     int bfC, bfD;
-    const double scale =
-        shell_quartet<C, LA, LB, LC, LD, BOYS, true, true>(t, p, g, s_bra_far, q, out, bfC, bfD);
-    digest(q, out, scale, bfC, bfD);
-  }
-  for (; it < nk; it += T) {
-    const int q = q0 + s_list[it];
-    double out[C::kOut];
-    int bfC, bfD;
-    const double scale =
-        shell_quartet<C, LA, LB, LC, LD, BOYS, true, false>(tl, p, g, s_bra, q, out, bfC, bfD);
-    digest(q, out, scale, bfC, bfD);
+    if (c >= far_chunk0) {
+      if (e != kEmpty) {
+        const double scale =
+            shell_quartet<C, LA, LB, LC, LD, BOYS, true, true>(t, p, g, s_bra_far, q, out, bfC, bfD);
+        digest(q, out, scale, bfC, bfD);
+      }
+    } else {
+      if (e != kEmpty) {
+        const double scale =
+            shell_quartet<C, LA, LB, LC, LD, BOYS, true, false>(tl, p, g, s_bra, q, out, bfC, bfD);
+        digest(q, out, scale, bfC, bfD);
+      }
+    }
   }
 
   // bra block of J: registers -> warp reduce -> one atomic per warp and component

@@ -53,7 +53,7 @@ def hostcheck():
     so = os.path.join(bdir, "libhostcheck.so")
     csrc = os.path.join(ROOT, "rchem_b200", "csrc")
     srcs = [os.path.join(ROOT, "tests", "hostcheck.cpp"), os.path.join(csrc, "basis_model.cpp")]
-    deps = srcs + [os.path.join(csrc, f) for f in ("eri_core.h", "pair_build.h", "basis_model.h")]
+    deps = srcs + [os.path.join(csrc, f) for f in ("eri_core.h", "pair_build.h", "basis_model.h", "boys_delta.h", "boys_delta_build.h")]
     deps.append(os.path.join(ROOT, "rchem_b200", "gen", "gen_eri.py"))
     gen = os.path.join(csrc, "gen", "eri_class_list.h")
     if not os.path.exists(gen) or os.path.getmtime(gen) < os.path.getmtime(deps[-1]):

@@ -94,7 +94,7 @@ void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const She
 using namespace rchem;
 
 struct AllTabs {
-  std::vector<double> exact, dthr;
+  std::vector<double> exact, dthr, ddirect;
   std::vector<float> drows;
   bool delta_ok = false;
   BoysTabs tabs(int L) const {
@@ -102,6 +102,7 @@ struct AllTabs {
     t.exact = exact.data() + (size_t)L * kBoysTableLen;
     t.delta.thr = dthr.data();
     t.delta.rows = drows.data();
+    t.delta.direct = ddirect.data();
     return t;
   }
 };
@@ -109,7 +110,7 @@ static const AllTabs& all_tabs() {
   static AllTabs T;
   if (T.exact.empty()) {
     build_boys_tables(&T.exact);
-    T.delta_ok = build_boys_delta_tables(&T.dthr, &T.drows);
+    T.delta_ok = build_boys_delta_tables(&T.dthr, &T.drows, &T.ddirect);
   }
   return T;
 }
@@ -192,19 +193,21 @@ extern "C" int hostcheck_ref_tables_ok() {
 extern "C" void hostcheck_boys(int boys, int L, double x, double* F) {
   const AllTabs& T = all_tabs();
   if (boys == 2) { boys_reference_faithful<8>(x, F); return; }
-  if (boys == 3 || boys == kBoysReference) {
-    double ex = 0.0;
+  if (boys == 3 || boys == kBoysReference) {  // the kernels' path (eri_core.h boys_reference)
     auto exact_x = [&]() { return x; };
     switch (L) {
-      case 0: boys_exact<0, true>(x, T.tabs(0).exact, F, &ex);
-              if (x < ref_exact_from(0) + 0.5) boys_reference_from_exact<0>(x, ex, T.tabs(0).delta, exact_x, F); break;
-      case 2: boys_exact<2, true>(x, T.tabs(2).exact, F, &ex);
-              if (x < ref_exact_from(2) + 0.5) boys_reference_from_exact<2>(x, ex, T.tabs(2).delta, exact_x, F); break;
-      case 4: boys_exact<4, true>(x, T.tabs(4).exact, F, &ex);
-              if (x < ref_exact_from(4) + 0.5) boys_reference_from_exact<4>(x, ex, T.tabs(4).delta, exact_x, F); break;
-      default: boys_exact<8, true>(x, T.tabs(8).exact, F, &ex);
-              if (x < ref_exact_from(8) + 0.5) boys_reference_from_exact<8>(x, ex, T.tabs(8).delta, exact_x, F); break;
+      case 0: boys_reference<0>(x, T.tabs(0), exact_x, F); break;
+      case 2: boys_reference<2>(x, T.tabs(2), exact_x, F); break;
+      case 4: boys_reference<4>(x, T.tabs(4), exact_x, F); break;
+      default: boys_reference<8>(x, T.tabs(8), exact_x, F); break;
     }
+    return;
+  }
+  if (boys == 5) {  // the other tabulated form: converged value minus tabulated truncation error
+    double ex = 0.0;
+    auto exact_x = [&]() { return x; };
+    boys_exact<8, true>(x, T.tabs(8).exact, F, &ex);
+    if (x < ref_exact_from(8) + 0.5) boys_reference_from_exact<8>(x, ex, T.tabs(8).delta, exact_x, F);
     return;
   }
   {
