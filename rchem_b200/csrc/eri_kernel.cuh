@@ -833,9 +833,13 @@ __device__ __forceinline__ void jk_light_body(const EriTask& t, long long blk, d
 #ifndef RCHEM_LIGHT_MINB
 #define RCHEM_LIGHT_MINB 6
 #endif
+#ifndef RCHEM_LIGHT_MINB_MED
+#define RCHEM_LIGHT_MINB_MED 1
+#endif
 template <int LA, int LB, int LC, int LD> struct LightCfg {
+  static constexpr int kTargets = EriClass<LA, LB, LC, LD>::kTargets;
   static constexpr int kMinBlocks =
-      EriClass<LA, LB, LC, LD>::kTargets <= 9 ? RCHEM_LIGHT_MINB : 1;
+      kTargets <= 9 ? RCHEM_LIGHT_MINB : (kTargets <= 18 ? RCHEM_LIGHT_MINB_MED : 1);
 };
 template <int LA, int LB, int LC, int LD, int BOYS>
 __global__ void __launch_bounds__(kThreads, LightCfg<LA, LB, LC, LD>::kMinBlocks)
