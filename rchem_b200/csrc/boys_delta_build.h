@@ -26,37 +26,7 @@ inline long double ld_boys_exact(int m, long double x) {
   return f;
 }
 
-// series branch: G_n(x) = sum_{j>=0} x^j / ((a)(a+1)..(a+n+1+j))
-inline long double ld_series_tail_g(int m, int n, long double x) {
-  const long double a = m + 0.5L;
-  long double c = 1.0L;
-  for (int i = 0; i <= n + 1; ++i) c /= (a + i);
-  long double term = c, sum = c;
-  for (int j = 1; j < 4000; ++j) {
-    term *= x / (a + n + 1 + j);
-    sum += term;
-    if (term < 1e-23L * sum) break;
-  }
-  return sum;
-}
-
-// fraction branch: delta = F_m - 0.5 (Gamma(a) x^-a - e^-x h_n(x)), h_n the n-th convergent
-inline long double ld_fraction_delta(int m, int n, long double x) {
-  const long double a = m + 0.5L;
-  long double gam = sqrtl(3.14159265358979323846264338327950288L);
-  for (int k = 0; k < m; ++k) gam *= (k + 0.5L);
-  const long double b0 = x + 1.0L - a;
-  long double A0 = 0.0L, A1 = 1.0L, B0 = 1.0L, B1 = b0;
-  for (int j = 1; j <= n; ++j) {
-    const long double aj = -(long double)j * (j - a), bj = b0 + 2.0L * j;
-    const long double A2 = bj * A1 + aj * A0, B2 = bj * B1 + aj * B0;
-    A0 = A1; A1 = A2; B0 = B1; B1 = B2;
-  }
-  const long double fref = 0.5L * (gam * powl(x, -a) - expl(-x) * (A1 / B1));
-  return ld_boys_exact(m, x) - fref;
-}
-
-// the reference's truncated functions themselves (boys_reference_direct)
+// the reference's truncated functions themselves, n = its iteration count on this side of the step
 inline long double ld_series_ref(int m, int n, long double x) {
   const long double a = m + 0.5L;
   long double term = 1.0L / a, sum = term;
@@ -107,88 +77,37 @@ inline void cheb_fit(Fn f, long double xc, long double h, Out* out) {
   }
 }
 
-// degree-5 interpolant at 6 Chebyshev nodes of [xc-h, xc+h], returned as coefficients of
-// (x - xc)^k
-template <class Fn> inline void cheb_fit6(Fn f, long double xc, long double h, float* out) {
-  long double V[6][7];
-  for (int j = 0; j < 6; ++j) {
-    const long double t = cosl((2 * j + 1) * 3.14159265358979323846264338327950288L / 12.0L);
-    long double p = 1.0L;
-    for (int k = 0; k < 6; ++k) { V[j][k] = p; p *= t; }
-    V[j][6] = f(xc + h * t);
-  }
-  for (int c = 0; c < 6; ++c) {  // Gaussian elimination with partial pivoting
-    int piv = c;
-    for (int r = c + 1; r < 6; ++r) if (fabsl(V[r][c]) > fabsl(V[piv][c])) piv = r;
-    for (int k = 0; k < 7; ++k) std::swap(V[c][k], V[piv][k]);
-    for (int r = 0; r < 6; ++r) {
-      if (r == c) continue;
-      const long double fct = V[r][c] / V[c][c];
-      for (int k = c; k < 7; ++k) V[r][k] -= fct * V[c][k];
-    }
-  }
-  long double hk = 1.0L;
-  for (int k = 0; k < 6; ++k) {
-    out[k] = (float)(V[k][6] / V[k][k] / hk);
-    hk *= h;
-  }
-  out[6] = out[7] = 0.0f;
-}
-
-// thr: [kRefMaxM+1][kDeltaCells] doubles; rows: [kRefMaxM+1][kDeltaMaxRows][kDeltaRowLen] floats.
-// Returns false if a cell holds more than one step or the layout limits are exceeded.
-// direct (optional): [kRefMaxM+1][kDeltaMaxRows][kDirectRowLen] doubles, the reference's Fgamma_m
-// itself per (cell, side) -- boys_reference_direct.
-inline bool build_boys_delta_tables(std::vector<double>* thr, std::vector<float>* rows,
-                                    std::vector<double>* direct = nullptr) {
-  thr->assign((size_t)(kRefMaxM + 1) * kDeltaCells, 0.0);
-  rows->assign((size_t)(kRefMaxM + 1) * kDeltaMaxRows * kDeltaRowLen, 0.0f);
-  if (direct) direct->assign((size_t)(kRefMaxM + 1) * kDeltaMaxRows * kDirectRowLen, 0.0);
+// thr: [kRefMaxM+1][kDeltaCells] doubles (first x above the cell's step; 1e300 = no step);
+// direct: [kRefMaxM+1][kDeltaCells][2][kDirectRowLen] doubles, the reference's Fgamma_m per
+// (cell, side of the step).  Returns false if a cell holds more than one step.
+inline bool build_boys_delta_tables(std::vector<double>* thr, std::vector<double>* direct) {
+  thr->assign((size_t)(kRefMaxM + 1) * kDeltaCells, 1e300);
+  direct->assign((size_t)(kRefMaxM + 1) * kDeltaCells * 2 * kDirectRowLen, 0.0);
   bool ok = true;
   for (int m = 0; m <= kRefMaxM; ++m) {
     const double a = m + 0.5;
-    const double cut = ref_exact_from_order(m) + 1.0;  // rows are needed below cut + 0.5
-    int before = 0;
+    const double cut = ref_exact_from_order(m) + 1.0;  // the reference's own steps matter below cut
     for (int c = 0; c < kDeltaCells; ++c) {
       const double lo = c < kDeltaFineCells ? c / 64.0 : (c - 192) / 16.0;
       const double hi = c < kDeltaFineCells ? (c + 1) / 64.0 : (c - 191) / 16.0;
-      double* t = thr->data() + (size_t)m * kDeltaCells + c;
-      auto encode = [&](double v, int n) {
-        long long b;
-        __builtin_memcpy(&b, &v, 8);
-        b = (b & ~4095LL) | (long long)(n & 31) | ((long long)(before & 127) << 5);
-        double r;
-        __builtin_memcpy(&r, &b, 8);
-        return r;
-      };
       const long double xc = 0.5L * ((long double)lo + hi), h = 0.5L * ((long double)hi - lo);
-      if (c == 0 || lo >= cut) {
-        *t = encode(1e300, 0);
-        if (direct && c + before < kDeltaMaxRows)  // converged F_m (cell 0 always takes the faithful loops)
-          cheb_fit<kDirectRowLen>([&](long double x) { return ld_boys_exact(m, x); }, xc, h,
-                                  direct->data() + ((size_t)m * kDeltaMaxRows + c + before) * kDirectRowLen);
+      double* rows = direct->data() + ((size_t)(m * kDeltaCells + c) * 2) * kDirectRowLen;
+      if (c == 0 || lo >= cut) {  // converged F_m (cell 0 always takes the faithful loops)
+        cheb_fit<kDirectRowLen>([&](long double x) { return ld_boys_exact(m, x); }, xc, h, rows);
+        for (int k = 0; k < kDirectRowLen; ++k) rows[kDirectRowLen + k] = rows[k];
         continue;
       }
       const bool series = lo < a + 1.0;
       const int n_lo = ref_iterations(m, lo), n_hi = ref_iterations(m, std::nextafter(hi, 0.0));
       const bool step = n_lo != n_hi;
       if (step && n_hi != n_lo + (series ? 1 : -1)) ok = false;
-      if (n_lo > 30 || before > 126) ok = false;
-      *t = encode(step ? ref_step(m, lo, std::nextafter(hi, 0.0), n_lo) : 1e300, n_lo);
-      for (int side = 0; side <= (step ? 1 : 0); ++side) {
+      if (step) (*thr)[(size_t)m * kDeltaCells + c] = ref_step(m, lo, std::nextafter(hi, 0.0), n_lo);
+      for (int side = 0; side < 2; ++side) {
         const int n = side ? n_hi : n_lo;
-        const size_t r = (size_t)m * kDeltaMaxRows + c + before + side;
-        if (c + before + side >= kDeltaMaxRows) { ok = false; break; }
-        float* out = rows->data() + r * kDeltaRowLen;
-        if (series) cheb_fit6([&](long double x) { return ld_series_tail_g(m, n, x); }, xc, h, out);
-        else cheb_fit6([&](long double x) { return ld_fraction_delta(m, n, x); }, xc, h, out);
-        if (direct) {
-          double* dout = direct->data() + r * kDirectRowLen;
-          if (series) cheb_fit<kDirectRowLen>([&](long double x) { return ld_series_ref(m, n, x); }, xc, h, dout);
-          else cheb_fit<kDirectRowLen>([&](long double x) { return ld_fraction_ref(m, n, x); }, xc, h, dout);
-        }
+        double* out = rows + side * kDirectRowLen;
+        if (series) cheb_fit<kDirectRowLen>([&](long double x) { return ld_series_ref(m, n, x); }, xc, h, out);
+        else cheb_fit<kDirectRowLen>([&](long double x) { return ld_fraction_ref(m, n, x); }, xc, h, out);
       }
-      if (step) ++before;
     }
   }
   return ok;

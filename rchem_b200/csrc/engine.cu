@@ -491,7 +491,6 @@ struct rchem_basis {
   double tasks_tau = -1.0;
   double* d_boys = nullptr;      // exact-Boys grids, one per L
   double* d_delta_thr = nullptr; // boys_delta.h tables
-  float* d_delta_rows = nullptr;
   double* d_delta_direct = nullptr;
   double *d_D = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
   double* d_dmax = nullptr;  // max|D| of the current build (device scalar)
@@ -625,7 +624,6 @@ void fill_common(const rchem_basis* h, EriTask* t) {
   t->N = h->N;
   t->boys.exact = h->d_boys;
   t->boys.delta.thr = h->d_delta_thr;
-  t->boys.delta.rows = h->d_delta_rows;
   t->boys.delta.direct = h->d_delta_direct;
   t->nranks = 1;
   t->far_sched = h->far_sched;
@@ -649,7 +647,7 @@ void release_device_state(rchem_basis* h) {
   }
   h->batches.clear();
   auto drop = [](auto*& ptr) { if (ptr) cudaFree(ptr); ptr = nullptr; };
-  drop(h->d_boys); drop(h->d_delta_thr); drop(h->d_delta_rows); drop(h->d_delta_direct); drop(h->d_D); drop(h->d_Kh);
+  drop(h->d_boys); drop(h->d_delta_thr); drop(h->d_delta_direct); drop(h->d_D); drop(h->d_Kh);
   drop(h->d_JK); drop(h->d_dmax); drop(h->d_light_tasks); drop(h->d_light_prefix);
   drop(h->d_fn_shell); drop(h->d_pair_key); drop(h->d_pair_fwd); drop(h->d_asym);
   if (h->h_light_tasks) cudaFreeHost(h->h_light_tasks);
@@ -703,15 +701,11 @@ int ensure_ready(rchem_basis* h) {
   build_boys_tables(&table);
   CUDA_OK(cudaMalloc(&h->d_boys, table.size() * sizeof(double)));
   CUDA_OK(cudaMemcpy(h->d_boys, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
-  std::vector<double> dthr;
-  std::vector<float> drows;
-  std::vector<double> ddirect;
-  if (!build_boys_delta_tables(&dthr, &drows, &ddirect))
-    return fail(RCHEM_ERR_CUDA, "internal: reference-Boys correction table layout exceeded");
+  std::vector<double> dthr, ddirect;
+  if (!build_boys_delta_tables(&dthr, &ddirect))
+    return fail(RCHEM_ERR_CUDA, "internal: reference-Boys table layout exceeded (two steps in one cell)");
   CUDA_OK(cudaMalloc(&h->d_delta_thr, dthr.size() * sizeof(double)));
-  CUDA_OK(cudaMalloc(&h->d_delta_rows, drows.size() * sizeof(float)));
   CUDA_OK(cudaMemcpy(h->d_delta_thr, dthr.data(), dthr.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(h->d_delta_rows, drows.data(), drows.size() * sizeof(float), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&h->d_delta_direct, ddirect.size() * sizeof(double)));
   CUDA_OK(cudaMemcpy(h->d_delta_direct, ddirect.data(), ddirect.size() * sizeof(double), cudaMemcpyHostToDevice));
 
@@ -1116,7 +1110,16 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
                 (unsigned)g.grid, g.smem, pick_stream()));
     st.launches += 1;
   }
-  for (TaskTable& tt : h->tasks) {
+  // Launch order: highest classes first.  Their launches are few, small-grid and long-running
+  // (one thread walks thousands of recurrence terms), so they should start early and overlap the
+  // bulk of the build instead of forming its tail (RCHEM_TASK_ORDER=0: table order, for A/B).
+  static const bool kReverseOrder = [] {
+    const char* e = std::getenv("RCHEM_TASK_ORDER");
+    return e ? atoi(e) != 0 : true;
+  }();
+  const size_t ntask = h->tasks.size();
+  for (size_t ti = 0; ti < ntask; ++ti) {
+    TaskTable& tt = h->tasks[kReverseOrder ? ntask - 1 - ti : ti];
     const Batch &B = h->batches[tt.bra], &K = h->batches[tt.ket];
     // J/K: (sp sp|sp sp) runs through its segmented twins; tensor / list modes never see them
     if (split ? tt.jk_skip : tt.sub) continue;

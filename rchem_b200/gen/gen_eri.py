@@ -38,6 +38,7 @@ AX = "xyz"
 # every primitive-quartet quantity (Boys values, the whole VRR) between its variants, which
 # only differ in the weight a VRR value is accumulated with.
 SP = 3
+SPLIT_TARGETS = 100  # classes with more contraction accumulators are emitted in parts (gen_class)
 
 
 def variants(t):
@@ -156,7 +157,7 @@ class VRR:
         return self.em.tmp(expr, flops)
 
 
-def gen_class(ta, tb, tc, td):
+def gen_class(ta, tb, tc, td, force_mono=False):
     L = lmax_of(ta) + lmax_of(tb) + lmax_of(tc) + lmax_of(td)
     # variants of the bra / ket shell pair: index = ia * nvar(B) + ib
     bra_vars = [(la, lb) for la in variants(ta) for lb in variants(tb)]
@@ -174,57 +175,74 @@ def gen_class(ta, tb, tc, td):
     nt = len(tindex)
 
     # ---- VRR ---------------------------------------------------------------
-    em = Emitter()
-    v = VRR(em)
-    acc_lines = []
-    for (vb, vk, e, f), idx in tindex.items():
-        name = v.val(e, f, 0)
-        if fused:
-            acc_lines.append(f"acc[{idx}] = fma(W[{vb * nvk + vk}], {name}, acc[{idx}]);")
-        else:
-            acc_lines.append(f"acc[{idx}] += {name};")
-    vrr_flops = em.flops + nt * (2 if fused else 1)  # one add (fma) per target for the contraction
-    vrr_body = em.lines + acc_lines
+    # Classes past SPLIT_TARGETS accumulators cannot live in registers: one straight-line function
+    # of several thousand values sends ptxas into its spill-everything fallback (32 registers,
+    # 30-70 kB of stack, FP64 pipe ~1 % busy on (dd|dd)).  Those classes are emitted in PARTS --
+    # one small __noinline__ function per bra component e (all ket targets of that e), each
+    # with its own memo table -- so every part is register-allocated on its own; the lower
+    # [e'0|f'0] values the parts share are recomputed (1.6-1.9x the flops of the monolithic form).
+    split = nt > SPLIT_TARGETS and not force_mono
+    groups = {}
+    for key in tindex:
+        groups.setdefault(key[2] if split else None, []).append(key)
+    vrr_parts = []
+    vrr_flops = 0
+    for keys in groups.values():
+        em = Emitter()
+        v = VRR(em)
+        acc_lines = []
+        for (vb, vk, e, f) in keys:
+            idx = tindex[(vb, vk, e, f)]
+            name = v.val(e, f, 0)
+            if fused:
+                acc_lines.append(f"acc[{idx}] = fma(W[{vb * nvk + vk}], {name}, acc[{idx}]);")
+            else:
+                acc_lines.append(f"acc[{idx}] += {name};")
+        vrr_flops += em.flops + len(keys) * (2 if fused else 1)  # one add (fma) per target for the contraction
+        vrr_parts.append(em.lines + acc_lines)
 
     # ---- HRR ---------------------------------------------------------------
-    hm = Emitter()
-    bmemo = {}
+    # (split classes: one part per bra function a, again with fresh memo tables)
+    st = {"hm": Emitter(), "bmemo": {}, "kmemo": {}}
 
     def hb(vb, vk, a, b, f):
         key = (vb, vk, a, b, f)
-        if key in bmemo:
-            return bmemo[key]
+        if key in st["bmemo"]:
+            return st["bmemo"][key]
         if sum(b) == 0:
             r = f"acc[{tindex[(vb, vk, a, f)]}]"
         else:
             i = next(k for k in range(3) if b[k] > 0)
             hi = hb(vb, vk, inc(a, i), dec(b, i), f)
             lo = hb(vb, vk, a, dec(b, i), f)
-            r = hm.tmp(f"fma(AB{AX[i]}, {lo}, {hi})", 2)
-        bmemo[key] = r
+            r = st["hm"].tmp(f"fma(AB{AX[i]}, {lo}, {hi})", 2)
+        st["bmemo"][key] = r
         return r
-
-    kmemo = {}
 
     def hk(vb, vk, a, b, c, d):
         key = (vb, vk, a, b, c, d)
-        if key in kmemo:
-            return kmemo[key]
+        if key in st["kmemo"]:
+            return st["kmemo"][key]
         if sum(d) == 0:
             r = hb(vb, vk, a, b, c)
         else:
             i = next(k for k in range(3) if d[k] > 0)
             hi = hk(vb, vk, a, b, inc(c, i), dec(d, i))
             lo = hk(vb, vk, a, b, c, dec(d, i))
-            r = hm.tmp(f"fma(CD{AX[i]}, {lo}, {hi})", 2)
-        kmemo[key] = r
+            r = st["hm"].tmp(f"fma(CD{AX[i]}, {lo}, {hi})", 2)
+        st["kmemo"][key] = r
         return r
 
-    out_lines = []
     fa, fb, fc, fd = functions(ta), functions(tb), functions(tc), functions(td)
     nout = len(fa) * len(fb) * len(fc) * len(fd)
+    hrr_parts = []
+    hrr_flops = 0
     o = 0
+    all_out = []
     for (ia, _, a) in fa:
+        out_lines = []
+        if split:
+            st = {"hm": Emitter(), "bmemo": {}, "kmemo": {}}
         for (ib, _, b) in fb:
             for (ic, _, c) in fc:
                 for (id_, _, d) in fd:
@@ -232,8 +250,14 @@ def gen_class(ta, tb, tc, td):
                     vk = ic * len(variants(td)) + id_
                     out_lines.append(f"out[{o}] = {hk(vb, vk, a, b, c, d)};")
                     o += 1
-    hrr_flops = hm.flops
-    hrr_body = hm.lines + out_lines
+        if split:
+            hrr_flops += st["hm"].flops
+            hrr_parts.append(st["hm"].lines + out_lines)
+        else:
+            all_out += out_lines
+    if not split:
+        hrr_flops = st["hm"].flops
+        hrr_parts.append(st["hm"].lines + all_out)
 
     tag = f"{ta}{tb}{tc}{td}"
     names = ["s", "p", "d", "sp"]
@@ -249,28 +273,52 @@ def gen_class(ta, tb, tc, td):
     src.append(f"  static constexpr int kNVk = {nvk};")
     src.append(f"  static constexpr int kVrrFlops = {vrr_flops};")
     src.append(f"  static constexpr int kHrrFlops = {hrr_flops};")
+    geom_names = ["PAx", "PAy", "PAz", "WPx", "WPy", "WPz", "QCx", "QCy", "QCz", "WQx", "WQy", "WQz",
+                  "oo2z", "oo2e", "oo2ze", "roz", "roe"]
+    wdecl = "const double* __restrict__ W, " if fused else ""
+    warg = "W, " if fused else ""
+
+    def emit_vrr(name, body, qual):
+        src.append(f"  {qual} static void {name}(const double* __restrict__ F, const VrrGeom& g, "
+                   f"{wdecl}double* __restrict__ acc) {{")
+        used = "\n".join(body)
+        for nm in geom_names:
+            if nm in used:
+                src.append(f"    const double {nm} = g.{nm};")
+        src.extend("    " + l for l in body)
+        src.append("  }")
+
+    def emit_hrr(name, body, qual):
+        src.append(f"  {qual} static void {name}(const double* __restrict__ acc, double ABx, double ABy, "
+                   "double ABz, double CDx, double CDy, double CDz, double* __restrict__ out) {")
+        src.append("    (void)ABx; (void)ABy; (void)ABz; (void)CDx; (void)CDy; (void)CDz;")
+        src.extend("    " + l for l in body)
+        src.append("  }")
+
     if fused:
         src.append("  // W[vb * kNVk + vk]: contraction weight of (bra variant vb, ket variant vk)")
-        src.append("  RCHEM_HD static void vrr(const double* __restrict__ F, const VrrGeom& g, "
-                   "const double* __restrict__ W, double* __restrict__ acc) {")
+    if not split:
+        emit_vrr("vrr", vrr_parts[0], "RCHEM_HD")
+        emit_hrr("hrr", hrr_parts[0], "RCHEM_HD")
     else:
-        src.append("  RCHEM_HD static void vrr(const double* __restrict__ F, const VrrGeom& g, "
-                   "double* __restrict__ acc) {")
-    used = "\n".join(vrr_body)
-    for nm in ["PAx", "PAy", "PAz", "WPx", "WPy", "WPz", "QCx", "QCy", "QCz", "WQx", "WQy", "WQz",
-               "oo2z", "oo2e", "oo2ze", "roz", "roe"]:
-        if nm in used:
-            src.append(f"    const double {nm} = g.{nm};")
-    src += ["    " + l for l in vrr_body]
-    src.append("  }")
-    src.append("  RCHEM_HD static void hrr(const double* __restrict__ acc, double ABx, double ABy, "
-               "double ABz, double CDx, double CDy, double CDz, double* __restrict__ out) {")
-    src.append("    (void)ABx; (void)ABy; (void)ABz; (void)CDx; (void)CDy; (void)CDz;")
-    src += ["    " + l for l in hrr_body]
-    src.append("  }")
+        src.append(f"  // emitted in {len(vrr_parts)} VRR parts (one per bra component) and {len(hrr_parts)} HRR parts "
+                   "(one per bra function): see gen_eri.py")
+        for k, body in enumerate(vrr_parts):
+            emit_vrr(f"vrr_part{k}", body, "RCHEM_PART")
+        emit_vrr("vrr", [f"vrr_part{k}(F, g, {warg}acc);" for k in range(len(vrr_parts))], "RCHEM_HD")
+        for k, body in enumerate(hrr_parts):
+            emit_hrr(f"hrr_part{k}", body, "RCHEM_PART")
+        emit_hrr("hrr", [f"hrr_part{k}(acc, ABx, ABy, ABz, CDx, CDy, CDz, out);" for k in range(len(hrr_parts))],
+                 "RCHEM_HD")
     src.append("};")
-    return tag, "\n".join(src) + "\n", dict(targets=nt, out=nout, vrr_flops=vrr_flops,
-                                             hrr_flops=hrr_flops)
+    info = dict(targets=nt, out=nout, vrr_flops=vrr_flops, hrr_flops=hrr_flops)
+    if split:
+        # the op-count MODEL is the monolithic form's; the parts recompute shared values
+        mono = gen_class(ta, tb, tc, td, force_mono=True)[2]
+        info = dict(targets=nt, out=nout, vrr_flops=mono["vrr_flops"], hrr_flops=mono["hrr_flops"],
+                    emitted_vrr_flops=vrr_flops, emitted_hrr_flops=hrr_flops,
+                    vrr_parts=len(vrr_parts), hrr_parts=len(hrr_parts))
+    return tag, "\n".join(src) + "\n", info
 
 
 def classes(lmax=LMAX):

@@ -95,13 +95,11 @@ using namespace rchem;
 
 struct AllTabs {
   std::vector<double> exact, dthr, ddirect;
-  std::vector<float> drows;
   bool delta_ok = false;
   BoysTabs tabs(int L) const {
     BoysTabs t;
     t.exact = exact.data() + (size_t)L * kBoysTableLen;
     t.delta.thr = dthr.data();
-    t.delta.rows = drows.data();
     t.delta.direct = ddirect.data();
     return t;
   }
@@ -110,7 +108,7 @@ static const AllTabs& all_tabs() {
   static AllTabs T;
   if (T.exact.empty()) {
     build_boys_tables(&T.exact);
-    T.delta_ok = build_boys_delta_tables(&T.dthr, &T.drows, &T.ddirect);
+    T.delta_ok = build_boys_delta_tables(&T.dthr, &T.ddirect);
   }
   return T;
 }
@@ -201,13 +199,6 @@ extern "C" void hostcheck_boys(int boys, int L, double x, double* F) {
       case 4: boys_reference<4>(x, T.tabs(4), exact_x, F); break;
       default: boys_reference<8>(x, T.tabs(8), exact_x, F); break;
     }
-    return;
-  }
-  if (boys == 5) {  // the other tabulated form: converged value minus tabulated truncation error
-    double ex = 0.0;
-    auto exact_x = [&]() { return x; };
-    boys_exact<8, true>(x, T.tabs(8).exact, F, &ex);
-    if (x < ref_exact_from(8) + 0.5) boys_reference_from_exact<8>(x, ex, T.tabs(8).delta, exact_x, F);
     return;
   }
   {

@@ -8,7 +8,7 @@ nw, bas, tau = int(sys.argv[1]), sys.argv[2], float(sys.argv[3])
 z, x = geo.water_cluster(nw)
 b = rc.Basis.new(z, x, bas)
 sa, sb, batch, Q = b.schwarz()
-bins = [0, 32, 128, 512, 1024, 2048, 4096, 8192, 1 << 30]
+bins = [0, 1, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 1 << 30]
 hist_pairs = np.zeros(len(bins) - 1); hist_q = np.zeros(len(bins) - 1); waste = 0.0; tot = 0.0
 for bi in np.unique(batch):
     Qb = Q[batch == bi]
