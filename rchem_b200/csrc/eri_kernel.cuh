@@ -205,8 +205,17 @@ __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const B
 // J and the D blocks it needs live PAIR-PACKED (BatchView::Jp / Dp), so lanes touch
 // consecutive addresses; finalize_j_kernel scatters Jp into the N x N matrix.
 // ---------------------------------------------------------------------------------------
+// Classes emitted in parts (> 100 accumulators, J/K through this kernel): few, long-running
+// threads whose time is the latency of one thread's serial work, so resident warps matter more
+// than registers (RCHEM_CHUNK_MINB_BIG blocks of 128 threads per SM: 1 = uncapped).
+#ifndef RCHEM_CHUNK_MINB_BIG
+#define RCHEM_CHUNK_MINB_BIG 1
+#endif
+template <int LA, int LB, int LC, int LD> struct ChunkCfg {
+  static constexpr int kMinBlocks = EriClass<LA, LB, LC, LD>::kTargets > 100 ? RCHEM_CHUNK_MINB_BIG : 1;
+};
 template <int LA, int LB, int LC, int LD, int BOYS, int MODE>
-__global__ void __launch_bounds__(kThreads) eri_kernel(const EriTask t) {
+__global__ void __launch_bounds__(kThreads, ChunkCfg<LA, LB, LC, LD>::kMinBlocks) eri_kernel(const EriTask t) {
   using C = EriClass<LA, LB, LC, LD>;
   constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
   constexpr bool kUnroll = C::kOut <= 81;
