@@ -372,6 +372,10 @@ __global__ void __launch_bounds__(kThreads, ChunkCfg<LA, LB, LC, LD>::kMinBlocks
 #ifndef RCHEM_BLK_PASSES
 #define RCHEM_BLK_PASSES 8
 #endif
+// large classes (> 18 targets) on a wide-row bra pair ((sp sp|: 160 kB of rows, one block per SM)
+#ifndef RCHEM_BLK_T_LARGE_WIDE
+#define RCHEM_BLK_T_LARGE_WIDE 256
+#endif
 #ifndef RCHEM_BLK_MINB_SMALL
 #define RCHEM_BLK_MINB_SMALL 2
 #endif
@@ -384,7 +388,8 @@ template <int LA, int LB, int LC, int LD> struct BlockCfg {
   // a fused (sp sp| bra pair has 8 D rows + 8 K rows in shared memory (160 kB at N = 1248): only
   // one block fits an SM, so medium classes of that kind run 512 threads in it
   static constexpr bool kWideRows = ncart(LA) + ncart(LB) >= 8;
-  static constexpr int kThreadsBlk = kSmall ? RCHEM_BLK_T_SMALL : ((kMedium && kWideRows) ? 512 : 256);
+  static constexpr int kThreadsBlk =
+      kSmall ? RCHEM_BLK_T_SMALL : ((kMedium && kWideRows) ? 512 : ((!kMedium && kWideRows) ? RCHEM_BLK_T_LARGE_WIDE : 256));
   static constexpr int kMinBlocks = kSmall ? RCHEM_BLK_MINB_SMALL : ((kMedium && !kWideRows) ? 2 : 1);
   static constexpr int kKetsPerBlock = kThreadsBlk * RCHEM_BLK_PASSES;
   static_assert(kKetsPerBlock <= 65535, "the block kernel's ket list holds 16-bit offsets");
