@@ -47,13 +47,8 @@ RCHEM_HD double delta_center(int cell) {
 
 RCHEM_HD void direct_row_load(const double* __restrict__ row, double* __restrict__ c) {
 #if defined(__CUDA_ARCH__)
-  const double2* r2 = reinterpret_cast<const double2*>(row);
-#pragma unroll
-  for (int j = 0; j < kDirectRowLen / 2; ++j) {
-    const double2 v = __ldg(r2 + j);
-    c[2 * j] = v.x;
-    c[2 * j + 1] = v.y;
-  }
+  ldg256(row, c);  // (eri_core.h: one 32-byte load per lane)
+  ldg256(row + 4, c + 4);
 #else
   for (int j = 0; j < kDirectRowLen; ++j) c[j] = row[j];
 #endif

@@ -944,9 +944,6 @@ int ensure_tasks(rchem_basis* h) {
       tt.smem_bytes = (size_t)2 * (ncart(B.la) + ncart(B.lb)) * h->N * sizeof(double) +
                       (size_t)B.K2 * B.prim_bytes() +
                       (size_t)(info.kets_per_block + 96) * sizeof(unsigned short) + 64;
-      // (A/B variant library built with -DRCHEM_BOYS_SMEM=1: room for the Boys grid slice)
-      static const bool kBoysSmem = std::getenv("RCHEM_BOYS_SMEM") && atoi(std::getenv("RCHEM_BOYS_SMEM"));
-      if (kBoysSmem) tt.smem_bytes += (size_t)kBoysTableLen * sizeof(double) + 16;
       // (the block and light kernels read the ket pair's functions from a packed 15 + 15 bit word)
       const bool packed_ok = h->N < 32768;
       const bool rows_fit = tt.smem_bytes <= kMaxBlockSmem && info.threads > 0 && packed_ok;

@@ -587,18 +587,10 @@ eri_jk_block_kernel(const EriTask t) {
       }
     }
   }
-#if RCHEM_BOYS_SMEM
-  // A/B variant (north star: "tabulated grids staged in shared memory"): this class's exact-Boys
-  // grid slice (61.5 kB) copied into the block's shared memory; the general code reads it there.
-  // Measured against the default (__ldg through L1/L2): profiles/r02_ab_boys_smem.txt.
-  double* s_boys = reinterpret_cast<double*>(
-      (reinterpret_cast<size_t>(s_list + BlockCfg<LA, LB, LC, LD>::kKetsPerBlock + 96) + 15) & ~(size_t)15);
-  for (int i = tid; i < kBoysTableLen; i += T) s_boys[i] = __ldg(t.boys.exact + i);
-  EriTask tl = t;
-  tl.boys.exact = s_boys;
-#else
+  // (The north-star variant -- this class's 61.5 kB exact-Boys grid slice staged in the block's
+  // shared memory -- was measured and lost: one block per SM instead of two, 111.6 vs 80.4 ms;
+  // profiles/r02_ab_dynamic_chunks_direct_boys.txt.  The grids stay in global memory / L2.)
   const EriTask& tl = t;
-#endif
   __syncthreads();
 
   // digestion of one evaluated shell quartet (bra pair p | ket pair q) into J and K
