@@ -12,8 +12,9 @@ for r in data:
 tot = sum(v.get('gpu__time_duration.sum', 0) for v in per.values())
 agg = collections.defaultdict(lambda: collections.defaultdict(float))
 for v in per.values():
-    m = re.search(r'eri_kernel<(\d+), (\d+), (\d+), (\d+), (\d+), (\d+)>', v['name'])
-    key = m.group(0) if m else v['name'][:40]
+    name = re.sub(r'^void ', '', v['name']).replace('rchem::', '').replace('(int)', '')
+    m = re.search(r'^\w+(<[^>]*>)?', name)
+    key = m.group(0) if m else name[:48]
     a = agg[key]; a['n'] += 1
     for k, x in v.items():
         if k == 'name': continue
@@ -23,4 +24,4 @@ print(f"total {tot/1e6:.3f} ms over {len(per)} launches")
 for k, a in sorted(agg.items(), key=lambda x: -x[1]['gpu__time_duration.sum']):
     t = a['gpu__time_duration.sum']
     extra = ' '.join(f"{kk.split('.')[0][-28:]}={vv:.3g}" for kk, vv in a.items() if kk not in ('n', 'gpu__time_duration.sum'))
-    print(f"{k:42s} {t/1e6:9.3f} ms {100*t/tot:5.1f}% n={int(a['n']):3d} {extra}")
+    print(f"{k:48s} {t/1e6:9.3f} ms {100*t/tot:5.1f}% n={int(a['n']):3d} {extra}")
