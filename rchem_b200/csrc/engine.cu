@@ -269,33 +269,53 @@ static void quartets_of_rank(TaskTable& tt, int rank, int nranks) {
   }
 }
 
-// D blocks of every shell pair of a batch, pair-major packed: Dp[ab][p] = D[bfA+a][bfB+b]
-__global__ void pack_d_kernel(const double* __restrict__ D, int N, const int* __restrict__ idx,
-                              int npairs, int stride, int nb, int ncomp, double* __restrict__ Dp) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= npairs) return;
-  const int bfA = idx[p], bfB = idx[stride + p];
-  for (int c = 0; c < ncomp; ++c)
-    Dp[(size_t)c * stride + p] = D[(size_t)(bfA + c / nb) * N + bfB + c % nb];
+// Per-batch view for the pack / finalise kernels, which cover EVERY batch in one launch (a build
+// used to spend ~0.9 ms of its critical path on 3 x 86 tiny launches and memsets: nothing at
+// N = 1, 8 % of the step at 8 GPUs, where every device repeats them).
+struct PackDesc {
+  const int* idx;
+  double* Dp;
+  double* Jp;
+  int npairs, stride, nb, ncomp;
+  int blk0;  // first thread block of this batch (256 pairs per block); desc[nbatch].blk0 = total
+};
+__device__ __forceinline__ int pack_desc_of_block(const PackDesc* __restrict__ desc, int nbatch, int blk) {
+  int lo = 0, hi = nbatch;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (desc[mid].blk0 <= blk) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// D blocks of every shell pair, pair-major packed: Dp[ab][p] = D[bfA+a][bfB+b]
+__global__ void pack_d_kernel(const double* __restrict__ D, int N, const PackDesc* __restrict__ desc,
+                              int nbatch) {
+  const PackDesc d = desc[pack_desc_of_block(desc, nbatch, blockIdx.x)];
+  const int p = (blockIdx.x - d.blk0) * blockDim.x + threadIdx.x;
+  if (p >= d.npairs) return;
+  const int bfA = d.idx[p], bfB = d.idx[d.stride + p];
+  for (int c = 0; c < d.ncomp; ++c)
+    d.Dp[(size_t)c * d.stride + p] = D[(size_t)(bfA + c / d.nb) * N + bfB + c % d.nb];
 }
 
 // J from the packed pair blocks: J[i][j] = J[j][i] += Jp[ab] (+ Jp[ba] on a diagonal shell pair,
-// whose block holds both orders) -- i.e. J = Jh + Jh^T of the digestion.  Inside one batch every
-// function pair belongs to exactly one shell pair, and the batches are finalised one after the
-// other on one stream, so the (non-atomic) accumulation is race-free; J starts from zero.  (The
-// segmented twins of fused (sp sp| pairs hold a second share of the same function pairs.)
-__global__ void finalize_j_kernel(const double* __restrict__ Jp, const int* __restrict__ idx,
-                                  int npairs, int stride, int nb, int ncomp, int N,
+// whose block holds both orders) -- i.e. J = Jh + Jh^T of the digestion.  A function pair can
+// receive shares from two batches (a fused (sp sp| pair and its segmented twins), so the
+// accumulation is atomic; J starts from zero.
+__global__ void finalize_j_kernel(const PackDesc* __restrict__ desc, int nbatch, int N,
                                   double* __restrict__ J) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= npairs) return;
-  const int bfA = idx[p], bfB = idx[stride + p], diag = idx[2 * stride + p];
-  for (int c = 0; c < ncomp; ++c) {
-    const int a = c / nb, b = c % nb;
-    double v = Jp[(size_t)c * stride + p];
-    if (diag) v += Jp[(size_t)(b * nb + a) * stride + p];
-    J[(size_t)(bfA + a) * N + bfB + b] += v;
-    if (!diag) J[(size_t)(bfB + b) * N + bfA + a] += v;
+  const PackDesc d = desc[pack_desc_of_block(desc, nbatch, blockIdx.x)];
+  const int p = (blockIdx.x - d.blk0) * blockDim.x + threadIdx.x;
+  if (p >= d.npairs) return;
+  const int bfA = d.idx[p], bfB = d.idx[d.stride + p], diag = d.idx[2 * d.stride + p];
+  for (int c = 0; c < d.ncomp; ++c) {
+    const int a = c / d.nb, b = c % d.nb;
+    double v = d.Jp[(size_t)c * d.stride + p];
+    if (diag) v += d.Jp[(size_t)(b * d.nb + a) * d.stride + p];
+    if (v == 0.0) continue;
+    atomicAdd(J + (size_t)(bfA + a) * N + bfB + b, v);
+    if (!diag) atomicAdd(J + (size_t)(bfB + b) * N + bfA + a, v);
   }
 }
 
@@ -519,6 +539,11 @@ struct rchem_basis {
   double* d_delta_direct = nullptr;
   double *d_D = nullptr, *d_Kh = nullptr, *d_JK = nullptr;
   double* d_dmax = nullptr;  // max|D| of the current build (device scalar)
+  // packed D / J blocks of all batches: two arenas, one descriptor table (pack_d / finalize_j)
+  double *d_Dp_all = nullptr, *d_Jp_all = nullptr;
+  size_t packed_doubles = 0;
+  PackDesc* d_pack_desc = nullptr;
+  int pack_blocks = 0;
   // merged light launches (one per class): task descriptors and block prefixes
   EriTask* d_light_tasks = nullptr;
   int* d_light_prefix = nullptr;
@@ -626,9 +651,6 @@ int upload_batch(rchem_basis* h, Batch& bt, const std::vector<int>& order) {
     CUDA_OK(cudaMalloc(&bt.d_bnd, bnd.size() * sizeof(float4)));
     CUDA_OK(cudaMalloc(&bt.d_zminf, zminf.size() * sizeof(float)));
     CUDA_OK(cudaMalloc(&bt.d_idx, idx.size() * sizeof(int)));
-    CUDA_OK(cudaMalloc(&bt.d_Dp, (size_t)bt.ncomp() * st * sizeof(double)));
-    CUDA_OK(cudaMalloc(&bt.d_Jp, (size_t)bt.ncomp() * st * sizeof(double)));
-    CUDA_OK(cudaMemset(bt.d_Dp, 0, (size_t)bt.ncomp() * st * sizeof(double)));
   }
   CUDA_OK(cudaMemcpyAsync(bt.d_prim, prim.data(), prim.size() * sizeof(double),
                           cudaMemcpyHostToDevice, h->stream));
@@ -668,12 +690,11 @@ void release_device_state(rchem_basis* h) {
   free_tasks(h);
   for (Batch& bt : h->batches) {
     cudaFree(bt.d_prim); cudaFree(bt.d_geom); cudaFree(bt.d_bnd); cudaFree(bt.d_zminf); cudaFree(bt.d_idx);
-    cudaFree(bt.d_Dp); cudaFree(bt.d_Jp);
   }
   h->batches.clear();
   auto drop = [](auto*& ptr) { if (ptr) cudaFree(ptr); ptr = nullptr; };
   drop(h->d_boys); drop(h->d_delta_thr); drop(h->d_delta_direct); drop(h->d_D); drop(h->d_Kh);
-  drop(h->d_JK); drop(h->d_dmax); drop(h->d_light_tasks); drop(h->d_light_prefix);
+  drop(h->d_JK); drop(h->d_dmax); drop(h->d_Dp_all); drop(h->d_Jp_all); drop(h->d_pack_desc); drop(h->d_light_tasks); drop(h->d_light_prefix);
   drop(h->d_fn_shell); drop(h->d_pair_key); drop(h->d_pair_fwd); drop(h->d_asym);
   if (h->h_light_tasks) cudaFreeHost(h->h_light_tasks);
   if (h->h_light_prefix) cudaFreeHost(h->h_light_prefix);
@@ -838,6 +859,31 @@ int ensure_ready(rchem_basis* h) {
     }
   }
 
+  {  // packed D / J blocks: one arena each, carved per batch (256-byte aligned slices)
+    size_t total = 0;
+    std::vector<size_t> off;
+    for (const Batch& bt : h->batches) {
+      off.push_back(total);
+      total += ((size_t)bt.ncomp() * bt.stride + 31) & ~(size_t)31;
+    }
+    h->packed_doubles = total;
+    CUDA_OK(cudaMalloc(&h->d_Dp_all, std::max<size_t>(1, total) * sizeof(double)));
+    CUDA_OK(cudaMalloc(&h->d_Jp_all, std::max<size_t>(1, total) * sizeof(double)));
+    CUDA_OK(cudaMemset(h->d_Dp_all, 0, std::max<size_t>(1, total) * sizeof(double)));
+    std::vector<PackDesc> desc;
+    int blk = 0;
+    for (size_t i = 0; i < h->batches.size(); ++i) {
+      Batch& bt = h->batches[i];
+      bt.d_Dp = h->d_Dp_all + off[i];
+      bt.d_Jp = h->d_Jp_all + off[i];
+      desc.push_back(PackDesc{bt.d_idx, bt.d_Dp, bt.d_Jp, bt.npairs, bt.stride, ncart(bt.lb), bt.ncomp(), blk});
+      blk += (bt.npairs + 255) / 256;
+    }
+    desc.push_back(PackDesc{nullptr, nullptr, nullptr, 0, 0, 1, 0, blk});
+    h->pack_blocks = blk;
+    CUDA_OK(cudaMalloc(&h->d_pack_desc, desc.size() * sizeof(PackDesc)));
+    CUDA_OK(cudaMemcpy(h->d_pack_desc, desc.data(), desc.size() * sizeof(PackDesc), cudaMemcpyHostToDevice));
+  }
   {  // Schwarz row sums for the K-row fixed-point bound (eri_kernel.cuh krow_add)
     std::vector<double> R(sh.size(), 0.0);
     for (const Batch& bt : h->batches)
@@ -1498,11 +1544,10 @@ static int jk_direct_device_impl(rchem_basis* h, const double* D_dev, double* JK
   const int N = h->N;
   // J.fill(0); K.fill(0) (basis.rs:389-390): the packed J blocks and the K half-accumulator
   CUDA_OK(cudaMemsetAsync(h->d_Kh, 0, nn * sizeof(double), h->stream));
-  for (const Batch& bt : h->batches) {
-    CUDA_OK(cudaMemsetAsync(bt.d_Jp, 0, (size_t)bt.ncomp() * bt.stride * sizeof(double), h->stream));
-    pack_d_kernel<<<(bt.npairs + 255) / 256, 256, 0, h->stream>>>(
-        D_dev, N, bt.d_idx, bt.npairs, bt.stride, ncart(bt.lb), bt.ncomp(), bt.d_Dp);
-  }
+  const int nbatch = (int)h->batches.size();
+  CUDA_OK(cudaMemsetAsync(h->d_Jp_all, 0, h->packed_doubles * sizeof(double), h->stream));
+  if (h->pack_blocks > 0)
+    pack_d_kernel<<<h->pack_blocks, 256, 0, h->stream>>>(D_dev, N, h->d_pack_desc, nbatch);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemsetAsync(h->d_dmax, 0, sizeof(double), h->stream));
   absmax_kernel<<<148, 256, 0, h->stream>>>(D_dev, nn, reinterpret_cast<unsigned long long*>(h->d_dmax));
@@ -1515,15 +1560,13 @@ static int jk_direct_device_impl(rchem_basis* h, const double* D_dev, double* JK
   rc = run_tasks(h, kModeJK, proto, rank, nranks);
   if (rc) return rc;
   if (!antisym) CUDA_OK(cudaMemsetAsync(JK_dev, 0, nn * sizeof(double), h->stream));
-  if (!antisym)
-    for (const Batch& bt : h->batches)
-      finalize_j_kernel<<<(bt.npairs + 255) / 256, 256, 0, h->stream>>>(
-          bt.d_Jp, bt.d_idx, bt.npairs, bt.stride, ncart(bt.lb), bt.ncomp(), N, JK_dev);
+  if (!antisym && h->pack_blocks > 0)
+    finalize_j_kernel<<<h->pack_blocks, 256, 0, h->stream>>>(h->d_pack_desc, nbatch, N, JK_dev);
   finalize_k_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, h->stream>>>(
       h->d_Kh, JK_dev + nn, N, antisym ? -1.0 : 1.0, antisym);
   CUDA_OK(cudaGetLastError());
-  // pack_d (+ finalize_j) per batch; absmax, finalize_k
-  h->stats.launches += (antisym ? 1 : 2) * (int)h->batches.size() + 2;
+  // pack_d (+ finalize_j), absmax, finalize_k
+  h->stats.launches += (antisym ? 1 : 2) + 2;
   CUDA_OK(cudaEventRecord(h->ev_stream, h->stream));
   h->last_stream = h->stream;
   h->last_stream_valid = true;
