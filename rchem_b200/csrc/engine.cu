@@ -1654,7 +1654,8 @@ int rchem_jk_inmem_device(int n, const double* I_dev, const double* D_dev, doubl
 // One handle, one call, n devices of this node:
 //   H2D of D once (device 0 of the group) -> peer copies of D over NVLink -> every device
 //   builds its block-interleaved share (one host thread per device enqueues its launches) ->
-//   device 0 sums the partial [J|K] out of its peers' memory (peer_reduce_kernel) -> ONE D2H.
+//   device i sums slice i of the partial [J|K] out of the others' memory (peer_reduce_kernel) and
+//   copies that slice to the host buffers over its own PCIe link (n concurrent D2H of 1/n each).
 // D must be symmetric on this path (an asymmetric D takes the one-device path).
 extern "C++" {
 namespace {
@@ -1713,47 +1714,90 @@ int jk_direct_multi(rchem_basis* h, double* J, double* K) {
     int r = ensure_ready(g);
     if (r) return r;
     CUDA_OK(cudaSetDevice(g->device));
+    if (!g->ev_done) CUDA_OK(cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming));
     if (i > 0) {
-      if (!g->ev_done) CUDA_OK(cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming));
       CUDA_OK(cudaStreamWaitEvent(g->stream, h->ev_D, 0));
       CUDA_OK(cudaMemcpyPeerAsync(g->d_D, g->device, h->d_D, h->device, nn * sizeof(double), g->stream));
     }
     r = jk_direct_device_impl(g, g->d_D, g->d_JK, i, n, 0);
     if (r) return r;
-    if (i > 0) CUDA_OK(cudaEventRecord(g->ev_done, g->stream));
+    CUDA_OK(cudaEventRecord(g->ev_done, g->stream));
     return RCHEM_OK;
   });
   if (rc) return rc;
-  CUDA_OK(cudaSetDevice(h->device));
-  // the sum, on device 0 of the group, straight from peer memory where the hardware allows it
-  PeerPtrs pp{};
-  h->peer_stage.resize(n - 1, nullptr);
-  for (int i = 1; i < n; ++i) {
-    rchem_basis* g = handle(i);
-    CUDA_OK(cudaStreamWaitEvent(h->stream, g->ev_done, 0));
-    int can = g->device == h->device;  // (same device only with RCHEM_MULTI_OVERSUBSCRIBE)
-    if (!can) {
-      CUDA_OK(cudaDeviceCanAccessPeer(&can, h->device, g->device));
-      if (can) {
-        cudaError_t e = cudaDeviceEnablePeerAccess(g->device, 0);
-        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
-        cudaGetLastError();
-      }
+
+  // Can every device of the group read every other one's memory?  (same physical device only
+  // with RCHEM_MULTI_OVERSUBSCRIBE)
+  bool all_p2p = true;
+  for (int i = 0; i < n && all_p2p; ++i)
+    for (int j = 0; j < n && all_p2p; ++j) {
+      const int di = handle(i)->device, dj = handle(j)->device;
+      if (di == dj) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, di, dj) != cudaSuccess || !can) all_p2p = false;
     }
-    if (can) {
-      pp.p[pp.n++] = reinterpret_cast<const double2*>(g->d_JK);
-    } else {
+  cudaGetLastError();
+
+  if (all_p2p) {
+    // Sharded epilogue: device i waits for every build, sums slice i of [J|K] straight out of the
+    // other devices' memory (NVLink peer loads) and copies that slice home over ITS OWN PCIe link,
+    // so the reduction and the device-to-host copy both shrink with the number of GPUs.
+    const size_t n2 = nn;  // [J|K] = 2 nn doubles = nn double2
+    rc = for_each_device(n, [&](int i) -> int {
+      rchem_basis* g = handle(i);
+      CUDA_OK(cudaSetDevice(g->device));
+      PeerPtrs pp{};
+      const size_t lo = n2 * (size_t)i / n, hi = n2 * (size_t)(i + 1) / n;
+      for (int j = 0; j < n; ++j) {
+        if (j == i) continue;
+        rchem_basis* o = handle(j);
+        CUDA_OK(cudaStreamWaitEvent(g->stream, o->ev_done, 0));
+        if (o->device != g->device) {
+          cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return fail(RCHEM_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+          cudaGetLastError();
+        }
+        pp.p[pp.n++] = reinterpret_cast<const double2*>(o->d_JK) + lo;
+      }
+      if (hi > lo) {
+        peer_reduce_kernel<<<148, 256, 0, g->stream>>>(reinterpret_cast<double2*>(g->d_JK) + lo, pp, hi - lo);
+        CUDA_OK(cudaGetLastError());
+        // doubles [2 lo, 2 hi) of [J|K]: the part below nn goes to J, the rest to K
+        const size_t a = 2 * lo, b = 2 * hi;
+        if (a < nn)
+          CUDA_OK(cudaMemcpyAsync(J + a, g->d_JK + a, (std::min(b, nn) - a) * sizeof(double),
+                                  cudaMemcpyDeviceToHost, g->stream));
+        if (b > nn) {
+          const size_t k0 = std::max(a, nn);
+          CUDA_OK(cudaMemcpyAsync(K + (k0 - nn), g->d_JK + k0, (b - k0) * sizeof(double),
+                                  cudaMemcpyDeviceToHost, g->stream));
+        }
+      }
+      CUDA_OK(cudaStreamSynchronize(g->stream));
+      return RCHEM_OK;
+    });
+    if (rc) return rc;
+    CUDA_OK(cudaSetDevice(h->device));
+  } else {
+    // No full peer access: device 0 of the group gathers staged copies and sums them.
+    CUDA_OK(cudaSetDevice(h->device));
+    PeerPtrs pp{};
+    h->peer_stage.resize(n - 1, nullptr);
+    for (int i = 1; i < n; ++i) {
+      rchem_basis* g = handle(i);
+      CUDA_OK(cudaStreamWaitEvent(h->stream, g->ev_done, 0));
       if (!h->peer_stage[i - 1]) CUDA_OK(cudaMalloc(&h->peer_stage[i - 1], 2 * nn * sizeof(double)));
       CUDA_OK(cudaMemcpyPeerAsync(h->peer_stage[i - 1], h->device, g->d_JK, g->device,
                                   2 * nn * sizeof(double), h->stream));
       pp.p[pp.n++] = reinterpret_cast<const double2*>(h->peer_stage[i - 1]);
     }
+    peer_reduce_kernel<<<148 * 4, 256, 0, h->stream>>>(reinterpret_cast<double2*>(h->d_JK), pp, nn);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(J, h->d_JK, nn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaMemcpyAsync(K, h->d_JK + nn, nn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
   }
-  peer_reduce_kernel<<<148 * 4, 256, 0, h->stream>>>(reinterpret_cast<double2*>(h->d_JK), pp, nn);
-  CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaMemcpyAsync(J, h->d_JK, nn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_OK(cudaMemcpyAsync(K, h->d_JK + nn, nn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_OK(cudaStreamSynchronize(h->stream));
   // whole-job statistics: counts summed over the group, launches likewise
   for (int i = 1; i < n; ++i) {
     const rchem_stats& s = handle(i)->stats;
@@ -1765,7 +1809,7 @@ int jk_direct_multi(rchem_basis* h, double* J, double* K) {
     h->stats.model_flops += s.model_flops;
     h->stats.launches += s.launches;
   }
-  h->stats.launches += 1;  // peer_reduce_kernel
+  h->stats.launches += all_p2p ? n : 1;  // peer_reduce_kernel
   return RCHEM_OK;
 }
 
