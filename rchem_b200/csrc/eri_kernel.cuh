@@ -207,9 +207,10 @@ __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const B
 // ---------------------------------------------------------------------------------------
 // Classes emitted in parts (> 100 accumulators, J/K through this kernel): few, long-running
 // threads whose time is the latency of one thread's serial work, so resident warps matter more
-// than registers (RCHEM_CHUNK_MINB_BIG blocks of 128 threads per SM: 1 = uncapped).
+// than registers (RCHEM_CHUNK_MINB_BIG blocks of 128 threads per SM; measured on (H2O)32/6-31G*:
+// 1 = uncapped 36.2 ms, 3: 34.8, 4 (128 registers): 33.9, 6: 33.5, 8: 33.6).
 #ifndef RCHEM_CHUNK_MINB_BIG
-#define RCHEM_CHUNK_MINB_BIG 1
+#define RCHEM_CHUNK_MINB_BIG 4
 #endif
 template <int LA, int LB, int LC, int LD> struct ChunkCfg {
   static constexpr int kMinBlocks = EriClass<LA, LB, LC, LD>::kTargets > 100 ? RCHEM_CHUNK_MINB_BIG : 1;
