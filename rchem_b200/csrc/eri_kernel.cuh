@@ -34,6 +34,14 @@
 
 namespace rchem {
 
+// integrals per shell quartet up to which the component scaling and the J/K digestion are fully
+// unrolled (static indices: the J/K partial sums stay in registers and out[] is addressed with
+// immediates); beyond it they are rolled loops with run-time div/mod over local-memory arrays.
+// Measured on (H2O)32/6-31G* (profiles/r02_ab_digest_unroll.txt): 81 -> 33.9 ms, 108 -> 29.8,
+// 216 -> 28.5, 324 -> 27.2, 1296 (= every class) -> 26.6 ms, for 50 s more build time.
+#ifndef RCHEM_UNROLL_MAX
+#define RCHEM_UNROLL_MAX 1296
+#endif
 constexpr int kThreads = 128;
 constexpr int kWarpsPerBlock = kThreads / 32;
 
@@ -137,7 +145,7 @@ __device__ __forceinline__ double shell_quartet(const EriTask& t, int p, const B
                                                 const PrimPairV<C::kNVb>* __restrict__ s_bra, int q,
                                                 double* __restrict__ out, int& bfC, int& bfD) {
   constexpr int NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
-  constexpr bool kUnroll = C::kOut <= 81;
+  constexpr bool kUnroll = C::kOut <= RCHEM_UNROLL_MAX;
   const double* gk = t.ket.geom + q;
   const int sk = t.ket.stride;
   const double Cx = __ldg(gk), Cy = __ldg(gk + sk), Cz = __ldg(gk + 2 * sk);
@@ -219,7 +227,7 @@ template <int LA, int LB, int LC, int LD, int BOYS, int MODE>
 __global__ void __launch_bounds__(kThreads, ChunkCfg<LA, LB, LC, LD>::kMinBlocks) eri_kernel(const EriTask t) {
   using C = EriClass<LA, LB, LC, LD>;
   constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
-  constexpr bool kUnroll = C::kOut <= 81;
+  constexpr bool kUnroll = C::kOut <= RCHEM_UNROLL_MAX;
 
   const int lane = threadIdx.x & 31;
   const long long w =
@@ -456,7 +464,7 @@ __global__ void __launch_bounds__(BlockCfg<LA, LB, LC, LD>::kThreadsBlk,
 eri_jk_block_kernel(const EriTask t) {
   using C = EriClass<LA, LB, LC, LD>;
   constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
-  constexpr bool kUnroll = C::kOut <= 81;
+  constexpr bool kUnroll = C::kOut <= RCHEM_UNROLL_MAX;
   constexpr int T = BlockCfg<LA, LB, LC, LD>::kThreadsBlk;
   // regimes a block sorts its kets into: far-field (proved), grid, grid + Fgamma correction
   constexpr int kRegimes = BOYS == kBoysReference ? 3 : 2;
@@ -695,7 +703,7 @@ template <int LA, int LB, int LC, int LD, int BOYS>
 __device__ __forceinline__ void jk_light_body(const EriTask& t, long long blk, double* smem) {
   using C = EriClass<LA, LB, LC, LD>;
   constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
-  constexpr bool kUnroll = C::kOut <= 81;
+  constexpr bool kUnroll = C::kOut <= RCHEM_UNROLL_MAX;
   constexpr int kRegimes = BOYS == kBoysReference ? 3 : 2;
 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
