@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -574,6 +575,8 @@ struct rchem_basis {
   std::vector<double*> peer_stage;  // on this device: copy of a peer's [J|K] when P2P loads are not possible
   cudaEvent_t ev_D = nullptr;       // D is resident on this device
   cudaEvent_t ev_done = nullptr;    // this handle's share of [J|K] is complete (peer side)
+  int group_p2p = -1;               // every device of the group can read every other one's memory (-1 = not probed)
+  bool peer_access_on = false;      // cudaDeviceEnablePeerAccess done from this handle's device
   double tasks_heavy = -1.0;        // values the task tables were built with
   int tasks_light = -1;
   // The tasks of one J/K (or tensor) build are independent kernels; they are spread over a
@@ -1709,79 +1712,88 @@ int jk_direct_multi(rchem_basis* h, double* J, double* K) {
   auto handle = [&](int i) { return i == 0 ? h : h->peers[i - 1]; };
   if (!h->ev_D) CUDA_OK(cudaEventCreateWithFlags(&h->ev_D, cudaEventDisableTiming));
   CUDA_OK(cudaEventRecord(h->ev_D, h->stream));
+
+  // Can every device of the group read every other one's memory?  (probed once per group; the
+  // same physical device appears twice only with RCHEM_MULTI_OVERSUBSCRIBE)
+  if (h->group_p2p < 0 || (int)h->peers.size() != n - 1) {
+    h->group_p2p = 1;
+    for (int i = 0; i < n && h->group_p2p; ++i)
+      for (int j = 0; j < n && h->group_p2p; ++j) {
+        const int di = handle(i)->device, dj = handle(j)->device;
+        if (di == dj) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, di, dj) != cudaSuccess || !can) h->group_p2p = 0;
+      }
+    cudaGetLastError();
+  }
+  const bool all_p2p = h->group_p2p == 1;
+
+  // One host thread per device for the whole call: enqueue the device's share of the build,
+  // meet the other threads (so every "build done" event exists), then -- with full peer access --
+  // the sharded epilogue: device i waits for every build, sums slice i of [J|K] straight out of
+  // the other devices' memory (NVLink peer loads) and copies that slice home over ITS OWN PCIe
+  // link, so the reduction and the device-to-host copy both shrink with the number of GPUs.
+  std::atomic<int> arrived{0}, failed{0};
   int rc = for_each_device(n, [&](int i) -> int {
     rchem_basis* g = handle(i);
-    int r = ensure_ready(g);
+    auto build = [&]() -> int {
+      int r = ensure_ready(g);
+      if (r) return r;
+      CUDA_OK(cudaSetDevice(g->device));
+      if (!g->ev_done) CUDA_OK(cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming));
+      if (i > 0) {
+        CUDA_OK(cudaStreamWaitEvent(g->stream, h->ev_D, 0));
+        CUDA_OK(cudaMemcpyPeerAsync(g->d_D, g->device, h->d_D, h->device, nn * sizeof(double), g->stream));
+      }
+      r = jk_direct_device_impl(g, g->d_D, g->d_JK, i, n, 0);
+      if (r) return r;
+      CUDA_OK(cudaEventRecord(g->ev_done, g->stream));
+      return RCHEM_OK;
+    };
+    const int r = build();
+    if (r) failed.fetch_add(1);
+    arrived.fetch_add(1);
+    while (arrived.load() < n) std::this_thread::yield();  // host-side meeting point
     if (r) return r;
-    CUDA_OK(cudaSetDevice(g->device));
-    if (!g->ev_done) CUDA_OK(cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming));
-    if (i > 0) {
-      CUDA_OK(cudaStreamWaitEvent(g->stream, h->ev_D, 0));
-      CUDA_OK(cudaMemcpyPeerAsync(g->d_D, g->device, h->d_D, h->device, nn * sizeof(double), g->stream));
+    if (failed.load() || !all_p2p) return RCHEM_OK;
+    PeerPtrs pp{};
+    const size_t n2 = nn;  // [J|K] = 2 nn doubles = nn double2
+    const size_t lo = n2 * (size_t)i / n, hi = n2 * (size_t)(i + 1) / n;
+    for (int j = 0; j < n; ++j) {
+      if (j == i) continue;
+      rchem_basis* o = handle(j);
+      CUDA_OK(cudaStreamWaitEvent(g->stream, o->ev_done, 0));
+      if (o->device != g->device && !g->peer_access_on) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(RCHEM_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      pp.p[pp.n++] = reinterpret_cast<const double2*>(o->d_JK) + lo;
     }
-    r = jk_direct_device_impl(g, g->d_D, g->d_JK, i, n, 0);
-    if (r) return r;
-    CUDA_OK(cudaEventRecord(g->ev_done, g->stream));
+    g->peer_access_on = true;
+    if (hi > lo) {
+      peer_reduce_kernel<<<148, 256, 0, g->stream>>>(reinterpret_cast<double2*>(g->d_JK) + lo, pp, hi - lo);
+      CUDA_OK(cudaGetLastError());
+      // doubles [2 lo, 2 hi) of [J|K]: the part below nn goes to J, the rest to K
+      const size_t a = 2 * lo, b = 2 * hi;
+      if (a < nn)
+        CUDA_OK(cudaMemcpyAsync(J + a, g->d_JK + a, (std::min(b, nn) - a) * sizeof(double),
+                                cudaMemcpyDeviceToHost, g->stream));
+      if (b > nn) {
+        const size_t k0 = std::max(a, nn);
+        CUDA_OK(cudaMemcpyAsync(K + (k0 - nn), g->d_JK + k0, (b - k0) * sizeof(double),
+                                cudaMemcpyDeviceToHost, g->stream));
+      }
+    }
+    CUDA_OK(cudaStreamSynchronize(g->stream));
     return RCHEM_OK;
   });
   if (rc) return rc;
+  CUDA_OK(cudaSetDevice(h->device));
 
-  // Can every device of the group read every other one's memory?  (same physical device only
-  // with RCHEM_MULTI_OVERSUBSCRIBE)
-  bool all_p2p = true;
-  for (int i = 0; i < n && all_p2p; ++i)
-    for (int j = 0; j < n && all_p2p; ++j) {
-      const int di = handle(i)->device, dj = handle(j)->device;
-      if (di == dj) continue;
-      int can = 0;
-      if (cudaDeviceCanAccessPeer(&can, di, dj) != cudaSuccess || !can) all_p2p = false;
-    }
-  cudaGetLastError();
-
-  if (all_p2p) {
-    // Sharded epilogue: device i waits for every build, sums slice i of [J|K] straight out of the
-    // other devices' memory (NVLink peer loads) and copies that slice home over ITS OWN PCIe link,
-    // so the reduction and the device-to-host copy both shrink with the number of GPUs.
-    const size_t n2 = nn;  // [J|K] = 2 nn doubles = nn double2
-    rc = for_each_device(n, [&](int i) -> int {
-      rchem_basis* g = handle(i);
-      CUDA_OK(cudaSetDevice(g->device));
-      PeerPtrs pp{};
-      const size_t lo = n2 * (size_t)i / n, hi = n2 * (size_t)(i + 1) / n;
-      for (int j = 0; j < n; ++j) {
-        if (j == i) continue;
-        rchem_basis* o = handle(j);
-        CUDA_OK(cudaStreamWaitEvent(g->stream, o->ev_done, 0));
-        if (o->device != g->device) {
-          cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
-          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
-            return fail(RCHEM_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
-          cudaGetLastError();
-        }
-        pp.p[pp.n++] = reinterpret_cast<const double2*>(o->d_JK) + lo;
-      }
-      if (hi > lo) {
-        peer_reduce_kernel<<<148, 256, 0, g->stream>>>(reinterpret_cast<double2*>(g->d_JK) + lo, pp, hi - lo);
-        CUDA_OK(cudaGetLastError());
-        // doubles [2 lo, 2 hi) of [J|K]: the part below nn goes to J, the rest to K
-        const size_t a = 2 * lo, b = 2 * hi;
-        if (a < nn)
-          CUDA_OK(cudaMemcpyAsync(J + a, g->d_JK + a, (std::min(b, nn) - a) * sizeof(double),
-                                  cudaMemcpyDeviceToHost, g->stream));
-        if (b > nn) {
-          const size_t k0 = std::max(a, nn);
-          CUDA_OK(cudaMemcpyAsync(K + (k0 - nn), g->d_JK + k0, (b - k0) * sizeof(double),
-                                  cudaMemcpyDeviceToHost, g->stream));
-        }
-      }
-      CUDA_OK(cudaStreamSynchronize(g->stream));
-      return RCHEM_OK;
-    });
-    if (rc) return rc;
-    CUDA_OK(cudaSetDevice(h->device));
-  } else {
+  if (!all_p2p) {
     // No full peer access: device 0 of the group gathers staged copies and sums them.
-    CUDA_OK(cudaSetDevice(h->device));
     PeerPtrs pp{};
     h->peer_stage.resize(n - 1, nullptr);
     for (int i = 1; i < n; ++i) {

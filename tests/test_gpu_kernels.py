@@ -359,7 +359,7 @@ def test_two_real_ranks_equal_one_gpu(rc, tmp_path):
 @pytest.mark.parametrize("ngpus", [2, 3])
 def test_jk_direct_drives_several_devices_from_one_call(rc, orc, geo, ref_or_restated, ngpus, monkeypatch):
     """JK_direct(&mut J, &mut K, &basis, &D) with RCHEM_OPT_NGPUS = n: one handle, one call,
-    n devices (block-interleaved shares, peer reduction on the first device, one D2H).  On a
+    n devices (block-interleaved shares, every device reducing and copying home its slice).  On a
     box with fewer GPUs the group wraps around the visible devices (RCHEM_MULTI_OVERSUBSCRIBE),
     which runs the same partition / peer-copy / reduction code."""
     if rc.device_count() < ngpus:
