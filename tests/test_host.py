@@ -352,6 +352,14 @@ def test_flop_model_is_generated(rc):
     assert fl["3333"]["vrr_flops"] < 0.65 * seg and fl["3333"]["out"] == 256
     assert fl["1111"]["hrr_flops"] == 324 and fl["2222"]["hrr_flops"] == 10586
     assert fl["1010"]["vrr_flops"] == 60
+    # classes past 100 accumulators are emitted in register-sized parts (one per bra component /
+    # bra function); the op-count MODEL stays the monolithic form's, the emitted code recomputes
+    # shared intermediates (< 2x)
+    assert "vrr_parts" not in fl["2120"] and fl["2120"]["targets"] == 96
+    for tag in ("2111", "2121", "2211", "2220", "2221", "2222", "3333"):
+        assert fl[tag]["targets"] > 100 and fl[tag]["vrr_parts"] >= 10 and fl[tag]["hrr_parts"] >= 4
+        assert fl[tag]["vrr_flops"] < fl[tag]["emitted_vrr_flops"] < 2.0 * fl[tag]["vrr_flops"]
+    assert fl["2222"]["vrr_parts"] == 31 and fl["2222"]["hrr_parts"] == 6
 
 
 # ---- multi-process host path (gloo, world_size 2) -------------------------------------------
