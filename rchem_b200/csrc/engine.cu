@@ -1135,6 +1135,9 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
         long long blocks = 0;
         for (const TaskTable* tt : kv.second) {
           EriTask t = make_task(*tt);
+#ifdef RCHEM_PROBES
+          if (std::getenv("RCHEM_PROBE_ALLFAR_LIGHT")) t.far_sched = 2;
+#endif
           t.lp = tt->d_lp;
           t.nlight = tt->nlight;
           t.light_cap = tt->light_cap;
@@ -1250,6 +1253,9 @@ int run_tasks(rchem_basis* h, int mode, EriTask proto, int rank, int nranks) {
       EriBlockInfo info{0, 0};
       EriBlockLaunchFn bfn = find_block_launcher(B.la, B.lb, K.la, K.lb, &info);
       t.nq = tt.d_nq;
+#ifdef RCHEM_PROBES
+      if (std::getenv("RCHEM_PROBE_ALLFAR_BLOCK")) t.far_sched = 2;
+#endif
       t.hp = tt.d_hp;
       t.hblk_prefix = tt.d_hblk_prefix;
       t.nheavy = tt.nheavy;
