@@ -560,6 +560,7 @@ struct rchem_basis {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_stream = nullptr;  // orders a build after the previous one across rchem_set_stream
   double* d_asym = nullptr;         // {max|D|, max|D - D^T|} of the host-buffer entry point
+  double* h_asym = nullptr;         // pinned copy of it (so the device-to-host copy never blocks the host)
   double setup_ms = 0.0;            // host wall time of pair build + Schwarz + task tables
   cudaStream_t last_stream = nullptr;  // stream of the previous build (order_after_previous_build)
   bool last_stream_valid = false;
@@ -699,6 +700,8 @@ void release_device_state(rchem_basis* h) {
   drop(h->d_boys); drop(h->d_delta_thr); drop(h->d_delta_direct); drop(h->d_D); drop(h->d_Kh);
   drop(h->d_JK); drop(h->d_dmax); drop(h->d_Dp_all); drop(h->d_Jp_all); drop(h->d_pack_desc); drop(h->d_light_tasks); drop(h->d_light_prefix);
   drop(h->d_fn_shell); drop(h->d_pair_key); drop(h->d_pair_fwd); drop(h->d_asym);
+  if (h->h_asym) cudaFreeHost(h->h_asym);
+  h->h_asym = nullptr;
   if (h->h_light_tasks) cudaFreeHost(h->h_light_tasks);
   if (h->h_light_prefix) cudaFreeHost(h->h_light_prefix);
   h->h_light_tasks = nullptr; h->h_light_prefix = nullptr; h->light_tasks_cap = 0;
@@ -899,6 +902,7 @@ int ensure_ready(rchem_basis* h) {
   }
   CUDA_OK(cudaMalloc(&h->d_dmax, sizeof(double)));
   CUDA_OK(cudaMalloc(&h->d_asym, 2 * sizeof(double)));
+  CUDA_OK(cudaMallocHost(&h->h_asym, 2 * sizeof(double)));
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_stream, cudaEventDisableTiming));
   h->last_stream_valid = false;
   const size_t nn = (size_t)h->N * h->N;
@@ -1851,9 +1855,22 @@ int rchem_jk_direct(rchem_basis* h, const double* D, double* J, double* K) {
   // antisymmetric parts, K(A) antisymmetric -- a second build, only when it is needed.
   CUDA_OK(cudaMemsetAsync(h->d_asym, 0, 2 * sizeof(double), h->stream));
   asym_probe_kernel<<<148, 256, 0, h->stream>>>(h->d_D, N, reinterpret_cast<unsigned long long*>(h->d_asym));
-  double probe[2] = {0.0, 0.0};
-  CUDA_OK(cudaMemcpyAsync(probe, h->d_asym, sizeof(probe), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  double* probe = h->h_asym;
+  probe[0] = probe[1] = 0.0;
+  CUDA_OK(cudaMemcpyAsync(probe, h->d_asym, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (h->ngpus > 1) {
+    // Several devices: do not wait for the probe.  The symmetric build is started at once, so the
+    // per-device host threads and their launches overlap the upload of D; the verdict is read
+    // after the call has finished anyway, and an asymmetric D (which the reference's caller never
+    // passes) then takes the one-device split path below.
+    rc = sync_peer_options(h);
+    if (rc) return rc;
+    rc = jk_direct_multi(h, J, K);  // (returns with h->stream drained: the probe has landed)
+    if (rc) return rc;
+    if (!(probe[1] > 1e-14 * std::max(probe[0], 1e-300))) return RCHEM_OK;
+  } else {
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  }
   if (probe[1] > 1e-14 * std::max(probe[0], 1e-300)) {
     if (h->symmetric_only)
       return fail(RCHEM_ERR_ASYMMETRIC_D, "JK_direct: the density matrix is not symmetric "
@@ -1878,10 +1895,6 @@ int rchem_jk_direct(rchem_basis* h, const double* D, double* J, double* K) {
     cudaStreamSynchronize(h->stream);
     cudaFree(dS); cudaFree(dA);
     if (rc) return rc;
-  } else if (h->ngpus > 1) {
-    rc = sync_peer_options(h);
-    if (rc) return rc;
-    return jk_direct_multi(h, J, K);
   } else {
     rc = rchem_jk_direct_device(h, h->d_D, h->d_JK, 0, 1);
     if (rc) return rc;

@@ -391,5 +391,13 @@ def test_jk_direct_drives_several_devices_from_one_call(rc, orc, geo, ref_or_res
     J, K = np.zeros((n, n)), np.zeros((n, n))
     rc.JK_direct(J, K, big, D)
     assert np.abs(J - J1).max() < 1e-13 and np.abs(K - K1).max() < 1e-13
-    # an asymmetric D falls back to the one-device path and still matches the reference loop
+    # an asymmetric D: the group starts the symmetric build optimistically (it does not wait for the
+    # symmetry probe), finds the verdict afterwards and redoes the build on the one-device split path
+    Da = D + 0.05 * np.triu(np.cos(np.arange(n * n, dtype=np.float64).reshape(n, n)), 1)
+    Jm, Km = np.zeros((n, n)), np.zeros((n, n))
+    rc.JK_direct(Jm, Km, big, Da)
     big.set_gpus(1)
+    Js, Ks = np.zeros((n, n)), np.zeros((n, n))
+    rc.JK_direct(Js, Ks, big, Da)
+    assert np.abs(Jm - Js).max() < 1e-13 and np.abs(Km - Ks).max() < 1e-13
+    assert np.abs(Ks - Ks.T).max() > 1e-6  # (K of an asymmetric D is not symmetric: the split path ran)
