@@ -849,7 +849,7 @@ __device__ __forceinline__ void jk_light_body(const EriTask& t, long long blk, d
 #define RCHEM_LIGHT_MINB 6
 #endif
 // medium classes (10-18 targets, ~220 registers uncapped): measured on (H2O)96/6-31G
-// 1 block of 128 threads per SM-quarter (uncapped) 80.6 ms, 3 (170 registers) 78.7 ms
+// 1 block of 128 threads per SM (uncapped) 80.6 ms, 3 (170 registers) 78.7 ms
 #ifndef RCHEM_LIGHT_MINB_MED
 #define RCHEM_LIGHT_MINB_MED 3
 #endif
