@@ -446,9 +446,8 @@ __device__ __forceinline__ double krow_get(const double* row, int n_row_doubles,
 }
 
 // A shell quartet is scheduled as far-field when the bounding spheres of its two shell pairs
-// prove x >= kFarProvenX for every primitive quartet (boys_exact switches to the asymptotic
-// form at kBoysXMax; the far-only code never looks at x again, so the proof must hold).
-constexpr float kFarProvenX = (float)kBoysXMax;
+// prove x >= far_proven_x(L) for every primitive quartet (eri_core.h: 36 / 40 / 48 by class; the
+// far-only code never looks at x again, so the proof must hold).
 
 
 // Scheduling regime of shell quartet (bra pair | ket pair q): quartet_regime_f (eri_core.h) on the
@@ -561,7 +560,7 @@ eri_jk_block_kernel(const EriTask t) {
     int pass = 0;
     for (int base = 0; base < nk; base += T, ++pass) {
       const int i = base + tid;
-      const int cls = i < nk ? quartet_regime_f<kRegimes>(bb, load_bound(t.ket, q0 + i), kFarProvenX, xcorr, t.far_sched) : 3;
+      const int cls = i < nk ? quartet_regime_f<kRegimes>(bb, load_bound(t.ket, q0 + i), (float)far_proven_x(C::kL), xcorr, t.far_sched) : 3;
       cls_bits |= (unsigned)cls << (2 * pass);
 #pragma unroll
       for (int c = 0; c < kRegimes; ++c) {
@@ -734,7 +733,7 @@ __device__ __forceinline__ void jk_light_body(const EriTask& t, long long blk, d
     int pass = 0;
     for (int base = 0; base < nq; base += 32, ++pass) {
       const int i = base + lane;
-      const int cls = i < nq ? quartet_regime_f<kRegimes>(bb, load_bound(t.ket, i), kFarProvenX, xcorr, t.far_sched) : 3;
+      const int cls = i < nq ? quartet_regime_f<kRegimes>(bb, load_bound(t.ket, i), (float)far_proven_x(C::kL), xcorr, t.far_sched) : 3;
       if (pass < 32) cls_bits |= (unsigned long long)cls << (2 * pass);
       n0 += __popc(__ballot_sync(0xffffffffu, cls == 0));
       n1 += __popc(__ballot_sync(0xffffffffu, cls == 1));
@@ -744,7 +743,7 @@ __device__ __forceinline__ void jk_light_body(const EriTask& t, long long blk, d
     for (int base = 0; base < nq; base += 32, ++pass) {
       const int i = base + lane;
       const int cls = pass < 32 ? (int)((cls_bits >> (2 * pass)) & 3)
-                                : (i < nq ? quartet_regime_f<kRegimes>(bb, load_bound(t.ket, i), kFarProvenX, xcorr, t.far_sched) : 3);
+                                : (i < nq ? quartet_regime_f<kRegimes>(bb, load_bound(t.ket, i), (float)far_proven_x(C::kL), xcorr, t.far_sched) : 3);
 #pragma unroll
       for (int c = 0; c < kRegimes; ++c) {
         const unsigned m = __ballot_sync(0xffffffffu, cls == c);

@@ -74,6 +74,8 @@ def hostcheck():
     H.hostcheck_ref_tables_ok.restype = C.c_int
     H.hostcheck_last_min_x.restype = C.c_double
     H.hostcheck_last_proved_far.restype = C.c_int
+    H.hostcheck_far_threshold.argtypes = [C.c_int]
+    H.hostcheck_far_threshold.restype = C.c_double
     H.hostcheck_last_prims_used.restype = C.c_int
     H.hostcheck_set_fuse.argtypes = [C.c_int]
     H.hostcheck_set_fuse.restype = None

@@ -69,7 +69,7 @@ void shell_quartet(const ShellSet& ss, const Shell& A, const Shell& B, const She
     // the kernels' own test (eri_core.h quartet_regime_f, single precision, conservative rounding)
     const PairBoundF fb = make_pair_bound_f(pb.M[0], pb.M[1], pb.M[2], pb.rad, pb.zmin);
     const PairBoundF fk = make_pair_bound_f(pk.M[0], pk.M[1], pk.M[2], pk.rad, pk.zmin);
-    g_proved_far = quartet_regime_f<2>(fb, fk, (float)kBoysXMax, 0.f, 1) == 0;
+    g_proved_far = quartet_regime_f<2>(fb, fk, (float)far_proven_x(C::kL), 0.f, 1) == 0;
   }
   for (const PrimPair& k : ket)
     for (const PrimPair& b : bra)
@@ -181,6 +181,7 @@ extern "C" int hostcheck_last_prims_used() { return g_prims_used; }
 extern "C" void hostcheck_set_fuse(int on) { g_fuse_sp = on; }
 extern "C" double hostcheck_last_min_x() { return g_min_x; }
 extern "C" int hostcheck_last_proved_far() { return g_proved_far; }
+extern "C" double hostcheck_far_threshold(int L) { return far_proven_x(L); }
 
 extern "C" int hostcheck_ref_tables_ok() {
   return all_tabs().delta_ok ? 1 : 0;
